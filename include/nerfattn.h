@@ -1,0 +1,178 @@
+/*
+ * nerfattn.h -- C ABI of libnerfattn.so, the B200 (sm_100a) replacement for the
+ * SIREN fit / reconstruction hot path of ruskaruma/nerf-attention.
+ *
+ * The reference has no FFI: its seam is the Python API.  Every
+ * entry point below therefore names the reference *Python* code it replaces
+ * (paths relative to the reference tree).  The Python drop-in
+ * (nerf-attention_b200/nerf_attention/_native.py) binds exactly these symbols
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside na_fit_t is a DEVICE pointer
+ *     owned by the caller; arrays of na_fit_t themselves live on the HOST
+ *   - all work is enqueued on the caller's stream and is asynchronous with
+ *     respect to the host; the library never synchronises the device
+ *   - return value 0 = success, negative = NA_ERR_*; nerfattn_last_error()
+ *     returns a thread-local message for the last failing call
+ *   - no global mutable state besides cached kernel attributes and the
+ *     thread-local error string: safe from several host threads on distinct
+ *     streams and distinct workspaces
+ */
+#ifndef NERFATTN_H_
+#define NERFATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFATTN_ABI_VERSION 3
+
+#if defined(__GNUC__)
+#define NA_API __attribute__((visibility("default")))
+#else
+#define NA_API
+#endif
+
+typedef struct CUstream_st* na_stream_t;      /* == cudaStream_t */
+
+enum {
+    NA_OK = 0,
+    NA_ERR_INVALID = -1,       /* bad argument (null pointer, non-positive size, ...)   */
+    NA_ERR_UNSUPPORTED = -2,   /* shape / precision outside what the kernels implement */
+    NA_ERR_WORKSPACE = -3,     /* workspace missing or too small                         */
+    NA_ERR_CUDA = -4           /* a CUDA runtime / driver call failed                    */
+};
+
+enum {
+    NA_PREC_FP32 = 0,          /* SIMT fp32 FMA everywhere: the parity mode (1e-5 / 1e-3) */
+    NA_PREC_TF32 = 1,          /* reserved; currently NA_ERR_UNSUPPORTED                   */
+    NA_PREC_BF16 = 2           /* tcgen05 BF16 x BF16 -> FP32 for the H->H / H->D layers;
+                                  layer 0, loss, Adam and master weights stay fp32        */
+};
+
+enum {
+    NA_FIT_TARGETS_PRENORMALISED = 1   /* targets already (t-mean)/std; mean/std are inputs */
+};
+
+/*
+ * One fit = one (layer, head, key|value, architecture) job of the sweep.
+ * Replaces the per-call state of reference fit_siren (nerf_attention/siren.py:80-93).
+ *
+ * params layout (fp32, nn.Linear [out,in] row-major, i.e. state_dict order,
+ * nerf_attention/siren.py:43-58):
+ *     W0[H,1] b0[H] { Wl[H,H] bl[H] } x L  Wf[D,H] bf[D]
+ * nerfattn_param_count() gives the total P.
+ */
+typedef struct na_fit {
+    int32_t N;                 /* seq_len, rows of the KV tensor                 */
+    int32_t D;                 /* head_dim, SIREN out_features                   */
+    int32_t H;                 /* SIRENConfig.hidden_features                    */
+    int32_t L;                 /* SIRENConfig.hidden_layers (H->H sine layers)   */
+    float   omega0;            /* SIRENConfig.omega_0                            */
+    int32_t flags;             /* NA_FIT_*                                        */
+    const float* positions;    /* [N]   as produced by torch.linspace(0,1,N)     */
+    const float* targets;      /* [N,D] raw KV tensor, row-major fp32            */
+    float* mean;               /* [D]   out: per-dim mean            (siren.py:85) */
+    float* std;                /* [D]   out: unbiased std, >= 1e-3   (siren.py:86) */
+    float* params;             /* [P]   in: initial weights, out: trained weights */
+    float* adam_m;             /* [P]   in/out, caller zero-fills before 1st call */
+    float* adam_v;             /* [P]   in/out, caller zero-fills before 1st call */
+    float* losses;             /* [epochs] out: normalised MSE per epoch (siren.py:105) */
+    float* cos_sims;           /* [N]   out: per-position CosSim    (siren.py:124) */
+    float* per_pos_mse;        /* [N]   out: per-position MSE       (siren.py:125) */
+    float* scalars;            /* [8]   out: final_mse, cos_mean, cos_min, cos_std(unbiased),
+                                          then 4 reserved                        */
+} na_fit_t;
+
+NA_API int         nerfattn_abi_version(void);
+NA_API const char* nerfattn_last_error(void);
+
+/* P = 2H + L(H*H+H) + (H*D + D); replaces SIREN.count_parameters (siren.py:63-64). */
+NA_API size_t nerfattn_param_count(int32_t H, int32_t L, int32_t D);
+
+/* Scratch bytes nerfattn_fit_batched needs for this job list and precision. */
+NA_API int nerfattn_fit_workspace_bytes(const na_fit_t* fits, int32_t nfits, int32_t precision,
+                                 size_t* bytes);
+
+/*
+ * Train every fit of the list for `epochs` full-batch Adam steps and write the
+ * final metrics.  Replaces the serial loop nest of fit_kv_cache
+ * (nerf_attention/fit.py:54-76) around fit_siren's normalisation, epoch loop
+ * and final evaluation (nerf_attention/siren.py:85-87, 98-105, 119-125), and
+ * torch.optim.Adam + CosineAnnealingLR underneath them.
+ *
+ *   lr_table   HOST array [epochs], float64: the learning rate optimizer.step()
+ *              uses at each epoch (the caller builds it from the real scheduler)
+ *   beta1/2, eps  Adam hyper-parameters (torch defaults 0.9, 0.999, 1e-8)
+ *   first_step 0-based count of Adam steps already applied to adam_m/adam_v
+ *              (0 for a fresh fit); step numbers continue from there
+ *   workspace  DEVICE scratch of >= nerfattn_fit_workspace_bytes() bytes,
+ *              256-byte aligned; contents undefined afterwards
+ */
+NA_API int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t epochs,
+                         const double* lr_table, double beta1, double beta2, double eps,
+                         int32_t first_step, int32_t precision,
+                         void* workspace, size_t workspace_bytes, na_stream_t stream);
+
+/*
+ * Full-sequence reconstruction out[i][N,D] = SIREN_i(positions) (optionally
+ * * std + mean).  Replaces model(positions) in profile_latency
+ * (nerf_attention/evaluate.py:196-200) and the reconstruction of
+ * plot_per_position_error (evaluate.py:148-152).  fp32 SIMT, no scratch.
+ * Only N, D, H, L, omega0, positions, params (and mean/std when denormalise
+ * != 0) of each na_fit_t are read.  `out` is a HOST array of n DEVICE pointers.
+ */
+NA_API int nerfattn_siren_forward(const na_fit_t* models, int32_t n, int32_t denormalise,
+                           float* const* out, void* workspace, size_t workspace_bytes,
+                           na_stream_t stream);
+NA_API int nerfattn_forward_workspace_bytes(const na_fit_t* models, int32_t n, size_t* bytes);
+
+/*
+ * Decode-step attention logits from the SIREN instead of the KV cache:
+ *     scores[i][t] = q[i] . (SIREN_i(pos_t) * std_i + mean_i),  t < N
+ * with the output layer folded into the query (DESIGN.md "decode"), so K is never
+ * materialised.  New functionality: the reference only times the unfused forward
+ * (evaluate.py:196-200) against a theoretical HBM read (evaluate.py:210-213).
+ *   q_fp16       DEVICE fp16 [n, D], the new token's query per head
+ *   scores       HOST array of n DEVICE pointers to fp32 [N]
+ *   precision    NA_PREC_FP32 (SIMT) or NA_PREC_BF16 (tcgen05 hidden layers)
+ *   reuse_setup  0: upload model table / bf16 weight mirror into the workspace, then run;
+ *                1: the workspace still holds the set-up of an earlier call with the same
+ *                   models (only q changed): run only -- this is the per-token cost
+ * All n models must share (N, D, H, L).  Reads N, D, H, L, omega0, positions, params,
+ * mean, std of each na_fit_t.
+ */
+NA_API int nerfattn_decode_workspace_bytes(const na_fit_t* key_models, int32_t n, int32_t precision,
+                                    size_t* bytes);
+NA_API int nerfattn_decode_qk(const na_fit_t* key_models, int32_t n, const void* q_fp16,
+                       float* const* scores, int32_t precision, int32_t reuse_setup,
+                       void* workspace, size_t workspace_bytes, na_stream_t stream);
+
+/*
+ * The baseline the SIREN decode is compared with: stream fp16 keys K[n,N,D]
+ * from HBM and compute scores[i*N+t] = q[i] . K[i][t] (fp32 accumulate).
+ * Replaces the constants raw_bytes/272e9 and raw_bytes/3350e9 of
+ * evaluate.py:210-211 with a measured, bandwidth-saturating read.
+ */
+NA_API int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float* scores,
+                       int32_t n, int32_t N, int32_t D, na_stream_t stream);
+
+/*
+ * Diagnostic: C[M,N] (fp32) = A x B with BF16 operands through the same
+ * tcgen05/TMA tile pipeline the BF16 fit uses.  a_mn_major / b_mn_major select
+ * the operand storage:  A is [M,K] row-major (0) or [K,M] row-major (1);
+ * B is [N,K] row-major (0) or [K,N] row-major (1).  Used by the tests to pin
+ * the shared-memory descriptors against a plain matmul.
+ */
+NA_API int nerfattn_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, float* c,
+                             int32_t M, int32_t N, int32_t K, int32_t batch,
+                             int32_t a_mn_major, int32_t b_mn_major, na_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFATTN_H_ */

@@ -1,0 +1,105 @@
+// Decode-side kernels: attention logits q.K for one new token, either from the
+// KV cache in HBM (the baseline) or from the SIREN that replaces it.
+//
+// Reference: evaluate.py:196-200 times the unfused SIREN forward and compares it
+// with bytes/bandwidth constants (evaluate.py:210-213).  Here both sides are real
+// kernels.  The SIREN side never materialises K:
+//     q.(std*(Wf h + bf) + mean) = (Wf^T (q*std)).h + q.(std*bf + mean) = u.h + c0
+// so the output layer (2 N H D flop, N D writes) collapses into one H-vector u per
+// head and the last sine layer's epilogue reduces u.sin(.) per position.
+#pragma once
+
+#include "common.cuh"
+
+namespace na {
+namespace dec {
+
+// ---------------------------------------------------------------------------
+// Baseline: scores[i][t] = q[i] . K[i][t],  K fp16 [n][N][D] streamed once from HBM.
+// G = D/8 lanes share a row (16 B per lane, one 128-bit load each), UNROLL rows in flight
+// per lane group; grid-stride over rows with a grid sized to a multiple of the SM count.
+template <int G>
+__global__ void __launch_bounds__(256)
+kvread_qk_kernel(const uint4* __restrict__ K, const uint4* __restrict__ q, float* __restrict__ scores,
+                 long long rows_total, int N) {
+    constexpr int UNROLL = 4;
+    const int lane_in_group = threadIdx.x % G;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngroups = (long long)gridDim.x * blockDim.x / G;
+    for (long long r0 = group * UNROLL; r0 < rows_total; r0 += ngroups * UNROLL) {
+        uint4 kv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long r = r0 + u;
+            kv[u] = (r < rows_total) ? __ldcs(K + r * G + lane_in_group) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long r = r0 + u;
+            const long long head = (r < rows_total) ? r / N : 0;
+            const uint4 qv = __ldg(q + head * G + lane_in_group);
+            const __half2* kh = reinterpret_cast<const __half2*>(&kv[u]);
+            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 kf = __half22float2(kh[j]), qf = __half22float2(qh[j]);
+                acc = fmaf(kf.x, qf.x, acc);
+                acc = fmaf(kf.y, qf.y, acc);
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
+            if (lane_in_group == 0 && r < rows_total) scores[r] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// u[i][j] = sum_d q[d] std[d] Wf[d][j],  c0[i] = sum_d q[d] (std[d] bf[d] + mean[d])
+__global__ void __launch_bounds__(256)
+decode_prep_kernel(const FitRec* recs, const __half* q, int D, int H, int wf_off, int bf_off, float* u, float* c0) {
+    const FitRec& rec = recs[blockIdx.x];
+    const __half* qi = q + (size_t)blockIdx.x * D;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float s = 0.f;
+        for (int d = 0; d < D; ++d)
+            s = fmaf(__half2float(qi[d]) * rec.stdv[d], rec.params[wf_off + (size_t)d * H + j], s);
+        u[(size_t)blockIdx.x * H + j] = s;
+    }
+    if (threadIdx.x < 32) {
+        float s = 0.f;
+        for (int d = threadIdx.x; d < D; d += 32)
+            s = fmaf(__half2float(qi[d]), fmaf(rec.stdv[d], rec.params[bf_off + d], rec.mean[d]), s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) c0[blockIdx.x] = s;
+    }
+}
+
+// scores[i][t] = c0[i] + sum_p part[i][p][t]
+__global__ void decode_finish_kernel(const float* part, int nparts, int N, const float* c0, float* const* scores) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const float* p = part + (size_t)blockIdx.y * nparts * N + t;
+    float s = c0[blockIdx.y];
+    for (int k = 0; k < nparts; ++k) s += p[(size_t)k * N];
+    scores[blockIdx.y][t] = s;
+}
+
+// hidden_layers == 0: the whole network is layer 0, so fuse it with the dot product.
+__global__ void __launch_bounds__(256)
+l0dot_kernel(const FitRec* recs, int N, int H, const float* u, const float* c0, float* const* scores) {
+    const FitRec& rec = recs[blockIdx.y];
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const float x = rec.pos[row];
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32)
+        s = fmaf(u[(size_t)blockIdx.y * H + j], sinf(rec.omega * fmaf(x, rec.params[j], rec.params[H + j])), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) scores[blockIdx.y][row] = s + c0[blockIdx.y];
+}
+
+}  // namespace dec
+}  // namespace na

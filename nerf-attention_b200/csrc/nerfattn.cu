@@ -1,0 +1,760 @@
+// libnerfattn.so -- C ABI + host orchestration (see include/nerfattn.h).
+//
+// nerfattn_fit_batched groups the job list by shape (N, D, H, L); all fits of a
+// group run through the same grouped kernels, one epoch of all groups is
+// captured once as a CUDA graph (groups on parallel branches) and replayed
+// `epochs` times with a device-side epoch counter -- no host sync, no per-epoch
+// launch storm (reference: ~45 launches + 1 sync per epoch, siren.py:98-105).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "siren_fp32.cuh"
+#include "siren_tc.cuh"
+#include "decode.cuh"
+
+namespace na {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && strcmp(v, "0") != 0;
+}
+
+// ------------------------------------------------------------------ planning
+struct Group {
+    int N, D, H, L, nf;
+    LayerMap lm;
+    int mtiles;            // row tiles of 128 (also the granularity of bias-gradient partials)
+    int nsplit, ksplit;    // split-K of the dW GEMMs (fp32 path)
+    std::vector<int> fit_idx;
+    FitRec* d_recs;
+    // activations / cos / dZ: [nf][N][H]; fp32 path uses float, tensor path bf16
+    void* act[kMaxHidden + 1];
+    void* cosb[kMaxHidden + 1];
+    void* dz[2];
+    void* dy;              // [nf][N][D]  (also y of the final evaluation: always fp32-sized)
+    float* yeval;          // [nf][N][D] fp32
+    float* evalact[2];     // fp32 ping-pong activations for the final fp32 forward (tensor mode)
+    float* gradpart;       // [nsplit][nf][P]
+    float* colpart; size_t colpart_layer_off[kMaxLayers];
+    float* xpart;          // [nf][mtiles][H]
+    float* losspart; int losspart_per_fit;
+    __nv_bfloat16* wbf16;  // [nf][P] bf16 mirror of the weights (tensor path)
+    tc::GroupMaps* maps;   // TMA descriptors (tensor path), host-side
+};
+
+struct Plan {
+    std::vector<Group> groups;
+    // unique target tensors
+    std::vector<const float*> uniq_ptr;
+    std::vector<int> uniq_N, uniq_D, uniq_prenorm, uniq_first_fit;
+    std::vector<size_t> uniq_tnorm_off, uniq_stat_off;
+    const float** d_uniq_ptr; int* d_uniq_prenorm;
+    float* tnorm; float* ustat_mean; float* ustat_std;
+    int* d_epoch; float* d_step_size; float* d_bc2;
+    size_t bytes;
+};
+
+static int validate(const na_fit_t* fits, int nfits, int precision) {
+    if (!fits || nfits <= 0) { set_error("fits must be a non-empty array"); return NA_ERR_INVALID; }
+    if (precision != NA_PREC_FP32 && precision != NA_PREC_BF16) {
+        set_error("precision %d not implemented (0 = fp32, 2 = bf16)", precision);
+        return NA_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < nfits; ++i) {
+        const na_fit_t& f = fits[i];
+        if (f.N < 2 || f.D < 1 || f.H < 1 || f.L < 0) { set_error("fit %d: bad shape", i); return NA_ERR_INVALID; }
+        if (f.L > kMaxHidden) { set_error("fit %d: hidden_layers %d > %d", i, f.L, kMaxHidden); return NA_ERR_UNSUPPORTED; }
+        if (f.H % 4 || f.D % 4) { set_error("fit %d: H and D must be multiples of 4", i); return NA_ERR_UNSUPPORTED; }
+        if (precision == NA_PREC_BF16 && !tc::shape_supported(f.N, f.D, f.H, f.L)) {
+            set_error("fit %d: bf16 path needs N %% 128 == 0, H in {64,128,256,512}, D %% 64 == 0 and D <= 256 "
+                      "(got N=%d D=%d H=%d)", i, f.N, f.D, f.H);
+            return NA_ERR_UNSUPPORTED;
+        }
+        if (!f.positions || !f.targets || !f.params) { set_error("fit %d: null pointer", i); return NA_ERR_INVALID; }
+    }
+    return NA_OK;
+}
+
+// Lay the workspace out.  With ws == nullptr this only computes sizes.
+static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision, void* ws, Plan& plan) {
+    Arena ar(ws);
+    std::map<std::tuple<int, int, int, int>, int> gid;
+    for (int i = 0; i < nfits; ++i) {
+        auto key = std::make_tuple(fits[i].N, fits[i].D, fits[i].H, fits[i].L);
+        auto it = gid.find(key);
+        if (it == gid.end()) {
+            Group g{};
+            g.N = fits[i].N; g.D = fits[i].D; g.H = fits[i].H; g.L = fits[i].L;
+            g.lm = make_layer_map(g.H, g.L, g.D);
+            it = gid.emplace(key, (int)plan.groups.size()).first;
+            plan.groups.push_back(g);
+        }
+        plan.groups[it->second].fit_idx.push_back(i);
+    }
+    // unique targets
+    std::map<std::tuple<const float*, int, int, int, const float*>, int> uid;
+    std::vector<int> fit_uniq(nfits);
+    size_t tnorm_total = 0, stat_total = 0;
+    for (int i = 0; i < nfits; ++i) {
+        const int pre = (fits[i].flags & NA_FIT_TARGETS_PRENORMALISED) ? 1 : 0;
+        auto key = std::make_tuple(fits[i].targets, fits[i].N, fits[i].D, pre, pre ? fits[i].mean : nullptr);
+        auto it = uid.find(key);
+        if (it == uid.end()) {
+            it = uid.emplace(key, (int)plan.uniq_ptr.size()).first;
+            plan.uniq_ptr.push_back(fits[i].targets);
+            plan.uniq_N.push_back(fits[i].N); plan.uniq_D.push_back(fits[i].D);
+            plan.uniq_prenorm.push_back(pre); plan.uniq_first_fit.push_back(i);
+            plan.uniq_tnorm_off.push_back(tnorm_total); plan.uniq_stat_off.push_back(stat_total);
+            tnorm_total += align_up((size_t)fits[i].N * fits[i].D, 64);
+            stat_total += align_up((size_t)fits[i].D, 64);
+        }
+        fit_uniq[i] = it->second;
+    }
+    const int nu = (int)plan.uniq_ptr.size();
+    plan.d_uniq_ptr = ar.take<const float*>(nu);
+    plan.d_uniq_prenorm = ar.take<int>(nu);
+    plan.tnorm = ar.take<float>(tnorm_total);
+    plan.ustat_mean = ar.take<float>(stat_total);
+    plan.ustat_std = ar.take<float>(stat_total);
+    plan.d_epoch = ar.take<int>(64);
+    plan.d_step_size = ar.take<float>(std::max(epochs, 1));
+    plan.d_bc2 = ar.take<float>(std::max(epochs, 1));
+
+    const bool bf = precision == NA_PREC_BF16;
+    const size_t esz = bf ? 2 : 4;
+    for (Group& g : plan.groups) {
+        g.nf = (int)g.fit_idx.size();
+        g.mtiles = ceil_div(g.N, 128);
+        g.d_recs = ar.take<FitRec>(g.nf);
+        const size_t nh = (size_t)g.nf * g.N * g.H, nd = (size_t)g.nf * g.N * g.D;
+        for (int l = 0; l <= g.L; ++l) {
+            g.act[l] = ar.take<char>(nh * esz);
+            g.cosb[l] = ar.take<char>(nh * esz);
+        }
+        g.dz[0] = ar.take<char>(nh * esz);
+        g.dz[1] = ar.take<char>(nh * esz);
+        g.dy = ar.take<char>(nd * esz);
+        g.yeval = ar.take<float>(nd);
+        if (bf) { g.evalact[0] = ar.take<float>(nh); g.evalact[1] = ar.take<float>(nh); }
+        // split-K of dW so that the launch has >= ~2 waves of CTAs (fp32 path only)
+        int out_tiles = 0;
+        for (int l = 1; l <= g.L + 1; ++l)
+            out_tiles = std::max(out_tiles, ceil_div(g.lm.out_dim[l], 128) * ceil_div(g.lm.in_dim[l], 128));
+        int want = bf ? 1 : std::max(1, (2 * 148 * 2) / std::max(1, g.nf * out_tiles));
+        int max_split = std::max(1, g.N / 256);
+        g.nsplit = std::min(want, max_split);
+        g.ksplit = (int)align_up((size_t)ceil_div(g.N, g.nsplit), 16);
+        g.nsplit = ceil_div(g.N, g.ksplit);
+        g.gradpart = ar.take<float>((size_t)g.nsplit * g.nf * g.lm.P);
+        size_t coff = 0;
+        for (int l = 0; l <= g.L + 1; ++l) {
+            g.colpart_layer_off[l] = coff;
+            coff += (size_t)g.nf * g.mtiles * g.lm.out_dim[l];
+        }
+        g.colpart = ar.take<float>(coff);
+        g.xpart = ar.take<float>((size_t)g.nf * g.mtiles * g.H);
+        g.losspart_per_fit = bf ? tc::loss_partials_per_fit(g.N, g.D) : g.mtiles * ceil_div(g.D, 128);
+        g.losspart = ar.take<float>((size_t)g.nf * g.losspart_per_fit);
+        g.wbf16 = bf ? ar.take<__nv_bfloat16>((size_t)g.nf * g.lm.P) : nullptr;
+        g.maps = nullptr;
+    }
+    plan.bytes = ar.bytes();
+    // stash per-fit unique ids in uniq_first_fit's tail: callers use fit_uniq via closure
+    plan.uniq_first_fit.insert(plan.uniq_first_fit.end(), fit_uniq.begin(), fit_uniq.end());
+}
+
+// ------------------------------------------------------------------ fp32 launches
+template <int MODE, bool AK, bool BK_>
+static void launch_sgemm(const f32::GemmArgs& a, int nf, int splits, cudaStream_t s) {
+    dim3 grid(ceil_div(a.N, f32::BN), ceil_div(a.M, f32::BM) * splits, nf);
+    f32::sgemm_kernel<MODE, AK, BK_><<<grid, f32::NTHREADS, 0, s>>>(a);
+}
+
+static void base_args(f32::GemmArgs& a, const Group& g) {
+    memset(&a, 0, sizeof(a));
+    a.recs = g.d_recs;
+    a.a_param_off = -1; a.b_param_off = -1;
+    a.loss_scale = 2.0f / ((float)g.N * (float)g.D);
+}
+
+// forward through the sine layers (fp32).  actbuf(l)/cosbuf(l) give the outputs of layer l.
+// `cosb` may be nullptr (evaluation / decode do not need the derivative factor); layers 1..last.
+static void fp32_forward_hidden(const Group& g, float* const* act, float* const* cosb, int last, cudaStream_t s) {
+    const size_t nh = (size_t)g.N * g.H;
+    {
+        const size_t total4 = nh / 4;
+        dim3 grid((unsigned)ceil_div(total4, (size_t)256), g.nf);
+        f32::layer0_kernel<float><<<grid, 256, 0, s>>>(g.d_recs, g.N, g.H, act[0], cosb ? cosb[0] : nullptr, nh);
+    }
+    for (int l = 1; l <= last; ++l) {
+        f32::GemmArgs a; base_args(a, g);
+        a.M = g.N; a.N = g.H; a.K = g.H;
+        a.A = act[l - 1]; a.a_fit = nh; a.lda = g.H;
+        a.b_param_off = g.lm.w_off[l]; a.ldb = g.H;
+        a.bias_off = g.lm.b_off[l];
+        a.out0 = act[l]; a.out0_fit = nh;
+        a.out1 = cosb ? cosb[l] : nullptr; a.out1_fit = nh;
+        launch_sgemm<f32::kFwdSine, true, true>(a, g.nf, 1, s);
+    }
+}
+
+static void fp32_output_layer(const Group& g, const float* actL, bool eval, cudaStream_t s,
+                              float* const* yout = nullptr, int denorm = 0) {
+    const size_t nh = (size_t)g.N * g.H, nd = (size_t)g.N * g.D;
+    f32::GemmArgs a; base_args(a, g);
+    a.M = g.N; a.N = g.D; a.K = g.H;
+    a.A = actL; a.a_fit = nh; a.lda = g.H;
+    a.b_param_off = g.lm.w_off[g.L + 1]; a.ldb = g.H;
+    a.bias_off = g.lm.b_off[g.L + 1];
+    if (eval) {
+        a.out0 = yout ? nullptr : g.yeval; a.out0_fit = nd;
+        a.yout = yout; a.denorm = denorm;
+        launch_sgemm<f32::kFwdEval, true, true>(a, g.nf, 1, s);
+    } else {
+        a.out0 = (float*)g.dy; a.out0_fit = nd;
+        a.colpart = g.colpart + g.colpart_layer_off[g.L + 1]; a.colpart_fit = (size_t)g.mtiles * g.D;
+        a.losspart = g.losspart; a.losspart_per_fit = g.losspart_per_fit;
+        launch_sgemm<f32::kFwdOut, true, true>(a, g.nf, 1, s);
+    }
+}
+
+static void launch_adam(const Group& g, const Plan& plan, double beta1, double beta2, double eps, cudaStream_t s) {
+    f32::AdamArgs a{};
+    a.recs = g.d_recs; a.lm = g.lm;
+    a.et.epoch = plan.d_epoch; a.et.step_size = plan.d_step_size; a.et.bc2_sqrt = plan.d_bc2;
+    a.gradpart = g.gradpart; a.grad_split_stride = (size_t)g.nf * g.lm.P; a.grad_fit = g.lm.P; a.nsplit = g.nsplit;
+    a.colpart = g.colpart;
+    for (int l = 0; l < kMaxLayers; ++l) a.colpart_layer_off[l] = g.colpart_layer_off[l];
+    for (int l = 0; l < kMaxLayers; ++l) a.col_mt[l] = (g.wbf16 && l > 0) ? 1 : g.mtiles;
+    a.xpart = g.xpart;
+    a.losspart = g.losspart; a.losspart_per_fit = g.losspart_per_fit;
+    a.loss_inv_count = 1.0f / ((float)g.N * (float)g.D);
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
+    a.wbf16 = g.wbf16; a.wbf16_fit = g.lm.P;
+    dim3 grid(ceil_div(g.lm.P, 256), g.nf);
+    f32::adam_kernel<<<grid, 256, 0, s>>>(a);
+}
+
+// one training epoch of one group, fp32 SIMT path
+static void fp32_epoch(const Group& g, const Plan& plan, double b1, double b2, double eps, cudaStream_t s) {
+    const size_t nh = (size_t)g.N * g.H, nd = (size_t)g.N * g.D;
+    float* act[kMaxHidden + 1]; float* cosb[kMaxHidden + 1];
+    for (int l = 0; l <= g.L; ++l) { act[l] = (float*)g.act[l]; cosb[l] = (float*)g.cosb[l]; }
+    fp32_forward_hidden(g, act, cosb, g.L, s);
+    fp32_output_layer(g, act[g.L], false, s);
+
+    // backward.  dz_cur holds dL/dz of layer `l`; for l = L+1 that is dY.
+    const float* dz_cur = (const float*)g.dy;
+    int cur_width = g.D;
+    for (int l = g.L + 1; l >= 1; --l) {
+        // dW_l = dz_l^T . act_{l-1}      [out_l x N] . [N x H]
+        {
+            f32::GemmArgs a; base_args(a, g);
+            a.M = g.lm.out_dim[l]; a.N = g.H; a.K = g.N;
+            a.A = dz_cur; a.a_fit = (size_t)g.N * cur_width; a.lda = cur_width;
+            a.B = act[l - 1]; a.b_fit = nh; a.ldb = g.H;
+            a.gradpart = g.gradpart; a.grad_split_stride = (size_t)g.nf * g.lm.P; a.grad_fit = g.lm.P;
+            a.grad_off = g.lm.w_off[l]; a.ksplit = g.ksplit;
+            launch_sgemm<f32::kDw, false, false>(a, g.nf, g.nsplit, s);
+        }
+        // dz_{l-1} = (dz_l . W_l) * omega * cos_{l-1}
+        {
+            f32::GemmArgs a; base_args(a, g);
+            a.M = g.N; a.N = g.H; a.K = g.lm.out_dim[l];
+            a.A = dz_cur; a.a_fit = (size_t)g.N * cur_width; a.lda = cur_width;
+            a.b_param_off = g.lm.w_off[l]; a.ldb = g.H;
+            float* dst = (float*)g.dz[(l - 1) & 1];
+            a.out0 = dst; a.out0_fit = nh;
+            a.cprev = cosb[l - 1]; a.cprev_fit = nh;
+            a.colpart = g.colpart + g.colpart_layer_off[l - 1]; a.colpart_fit = (size_t)g.mtiles * g.H;
+            if (l == 1) { a.xpart = g.xpart; a.xpart_fit = (size_t)g.mtiles * g.H; }
+            launch_sgemm<f32::kDx, true, false>(a, g.nf, 1, s);
+            dz_cur = dst; cur_width = g.H;
+        }
+    }
+    (void)nd;
+    launch_adam(g, plan, b1, b2, eps, s);
+}
+
+// final evaluation: fp32 forward with the trained weights + metrics (siren.py:119-125).
+// Always fp32 SIMT, also in the BF16 mode: the numbers must be what torch's model(positions)
+// gives for the returned weights.
+static void final_eval(const Group& g, int precision, cudaStream_t s) {
+    float* act[kMaxHidden + 1];
+    for (int l = 0; l <= g.L; ++l)
+        act[l] = (precision == NA_PREC_FP32) ? (float*)g.act[l] : g.evalact[l & 1];
+    fp32_forward_hidden(g, act, nullptr, g.L, s);
+    fp32_output_layer(g, act[g.L], true, s);
+    dim3 grid(ceil_div(g.N, 8), g.nf);
+    f32::row_metrics_kernel<<<grid, 256, 0, s>>>(g.d_recs, g.yeval, (size_t)g.N * g.D, g.N, g.D);
+    f32::fit_scalars_kernel<<<g.nf, 256, 0, s>>>(g.d_recs, g.N);
+}
+
+// Executable graphs may still be running when nerfattn_fit_batched returns (the library never
+// synchronises).  They are parked here with an event and destroyed by a later call once done.
+struct Parked { cudaGraphExec_t exec; cudaGraph_t graph; cudaEvent_t done; };
+static std::mutex g_park_mu;
+static std::vector<Parked> g_parked;
+static void park_graph(cudaGraphExec_t exec, cudaGraph_t graph, cudaStream_t stream) {
+    Parked p{exec, graph, nullptr};
+    cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming);
+    cudaEventRecord(p.done, stream);
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    g_parked.push_back(p);
+}
+static void reap_graphs() {
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    for (size_t i = 0; i < g_parked.size();) {
+        if (cudaEventQuery(g_parked[i].done) == cudaSuccess) {
+            cudaGraphExecDestroy(g_parked[i].exec);
+            cudaGraphDestroy(g_parked[i].graph);
+            cudaEventDestroy(g_parked[i].done);
+            g_parked[i] = g_parked.back();
+            g_parked.pop_back();
+        } else ++i;
+    }
+    cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error of ours
+}
+
+}  // namespace na
+
+// =========================================================================== C ABI
+using namespace na;
+
+extern "C" int nerfattn_abi_version(void) { return NERFATTN_ABI_VERSION; }
+extern "C" const char* nerfattn_last_error(void) { return g_err; }
+
+extern "C" size_t nerfattn_param_count(int32_t H, int32_t L, int32_t D) {
+    return (size_t)2 * H + (size_t)L * ((size_t)H * H + H) + (size_t)H * D + D;
+}
+
+extern "C" int nerfattn_fit_workspace_bytes(const na_fit_t* fits, int32_t nfits, int32_t precision, size_t* bytes) {
+    if (!bytes) { set_error("bytes is null"); return NA_ERR_INVALID; }
+    int rc = validate(fits, nfits, precision);
+    if (rc) return rc;
+    Plan plan{};
+    make_plan(fits, nfits, 1 << 20, precision, nullptr, plan);   // tables sized for up to 1M epochs
+    *bytes = plan.bytes;
+    return NA_OK;
+}
+
+extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t epochs, const double* lr_table,
+                                    double beta1, double beta2, double eps, int32_t first_step,
+                                    int32_t precision, void* workspace, size_t workspace_bytes,
+                                    na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    reap_graphs();
+    int rc = validate(fits, nfits, precision);
+    if (rc) return rc;
+    if (epochs < 0 || epochs > (1 << 20) || (epochs > 0 && !lr_table)) { set_error("bad epochs / lr_table"); return NA_ERR_INVALID; }
+    for (int i = 0; i < nfits; ++i) {
+        const na_fit_t& f = fits[i];
+        if (!f.mean || !f.std || !f.adam_m || !f.adam_v || !f.cos_sims || !f.per_pos_mse || !f.scalars ||
+            (epochs > 0 && !f.losses)) { set_error("fit %d: null output pointer", i); return NA_ERR_INVALID; }
+    }
+    if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return NA_ERR_WORKSPACE; }
+    Plan plan{};
+    make_plan(fits, nfits, 1 << 20, precision, workspace, plan);
+    if (plan.bytes > workspace_bytes) {
+        set_error("workspace too small: need %zu bytes, got %zu", plan.bytes, workspace_bytes);
+        return NA_ERR_WORKSPACE;
+    }
+    const int nu = (int)plan.uniq_ptr.size();
+    const int* fit_uniq = plan.uniq_first_fit.data() + nu;
+
+    // ---- host tables -> device
+    NA_CUDA_OK(cudaMemcpyAsync(plan.d_uniq_ptr, plan.uniq_ptr.data(), nu * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    NA_CUDA_OK(cudaMemcpyAsync(plan.d_uniq_prenorm, plan.uniq_prenorm.data(), nu * sizeof(int), cudaMemcpyHostToDevice, stream));
+    NA_CUDA_OK(cudaMemsetAsync(plan.d_epoch, 0, sizeof(int), stream));
+    if (epochs > 0) {
+        std::vector<float> ss(epochs), bc2(epochs);
+        for (int e = 0; e < epochs; ++e) {          // torch/optim/adam.py: python-float (double) math
+            const double t = (double)(first_step + e + 1);
+            ss[e] = (float)(lr_table[e] / (1.0 - std::pow(beta1, t)));
+            bc2[e] = (float)std::sqrt(1.0 - std::pow(beta2, t));
+        }
+        NA_CUDA_OK(cudaMemcpyAsync(plan.d_step_size, ss.data(), epochs * sizeof(float), cudaMemcpyHostToDevice, stream));
+        NA_CUDA_OK(cudaMemcpyAsync(plan.d_bc2, bc2.data(), epochs * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
+    for (Group& g : plan.groups) {
+        std::vector<FitRec> recs(g.nf);
+        for (int k = 0; k < g.nf; ++k) {
+            const na_fit_t& f = fits[g.fit_idx[k]];
+            const int u = fit_uniq[g.fit_idx[k]];
+            FitRec& r = recs[k];
+            r.pos = f.positions; r.traw = f.targets;
+            r.tnorm = plan.tnorm + plan.uniq_tnorm_off[u];
+            r.mean = plan.ustat_mean + plan.uniq_stat_off[u];
+            r.stdv = plan.ustat_std + plan.uniq_stat_off[u];
+            r.params = f.params; r.m = f.adam_m; r.v = f.adam_v; r.losses = f.losses;
+            r.cos = f.cos_sims; r.ppmse = f.per_pos_mse; r.scalars = f.scalars;
+            r.mean_out = f.mean; r.std_out = f.std; r.omega = f.omega0; r.uniq = u;
+        }
+        NA_CUDA_OK(cudaMemcpyAsync(g.d_recs, recs.data(), g.nf * sizeof(FitRec), cudaMemcpyHostToDevice, stream));
+    }
+    // pre-normalised targets carry their statistics in: copy them into the per-tensor slots
+    for (int u = 0; u < nu; ++u) {
+        if (!plan.uniq_prenorm[u]) continue;
+        const na_fit_t& f = fits[plan.uniq_first_fit[u]];
+        NA_CUDA_OK(cudaMemcpyAsync(plan.ustat_mean + plan.uniq_stat_off[u], f.mean, f.D * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        NA_CUDA_OK(cudaMemcpyAsync(plan.ustat_std + plan.uniq_stat_off[u], f.std, f.D * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+    // ---- normalisation: one launch per unique tensor shape class (usually one)
+    for (int u = 0; u < nu;) {
+        int v = u;
+        while (v < nu && plan.uniq_N[v] == plan.uniq_N[u] && plan.uniq_D[v] == plan.uniq_D[u] &&
+               plan.uniq_tnorm_off[v] - plan.uniq_tnorm_off[u] == (size_t)(v - u) * align_up((size_t)plan.uniq_N[u] * plan.uniq_D[u], 64))
+            ++v;
+        f32::NormArgs a{};
+        a.traw = plan.d_uniq_ptr + u;
+        a.tnorm = plan.tnorm + plan.uniq_tnorm_off[u];
+        a.tnorm_stride = align_up((size_t)plan.uniq_N[u] * plan.uniq_D[u], 64);
+        a.mean = plan.ustat_mean + plan.uniq_stat_off[u];
+        a.stdv = plan.ustat_std + plan.uniq_stat_off[u];
+        a.prenorm = plan.d_uniq_prenorm + u;
+        a.N = plan.uniq_N[u]; a.D = plan.uniq_D[u];
+        // stats stride must equal align_up(D,64) per tensor: norm_kernel indexes mean[u*D+d], so
+        // launch per tensor when D is not a multiple of 64
+        if (a.D % 64 == 0) {
+            dim3 grid(ceil_div(a.D, 32), v - u);
+            f32::norm_kernel<<<grid, dim3(32, 32), 0, stream>>>(a);
+        } else {
+            for (int w = u; w < v; ++w) {
+                f32::NormArgs b = a;
+                b.traw = plan.d_uniq_ptr + w;
+                b.tnorm = plan.tnorm + plan.uniq_tnorm_off[w];
+                b.mean = plan.ustat_mean + plan.uniq_stat_off[w];
+                b.stdv = plan.ustat_std + plan.uniq_stat_off[w];
+                b.prenorm = plan.d_uniq_prenorm + w;
+                dim3 grid(ceil_div(b.D, 32), 1);
+                f32::norm_kernel<<<grid, dim3(32, 32), 0, stream>>>(b);
+            }
+        }
+        NA_LAUNCH_OK("norm_kernel");
+        u = v;
+    }
+    for (Group& g : plan.groups) {
+        f32::scatter_stats_kernel<<<g.nf, 128, 0, stream>>>(g.d_recs, g.D);
+        NA_LAUNCH_OK("scatter_stats_kernel");
+    }
+
+    // ---- tensor path set-up: TMA descriptors + initial bf16 weight mirror
+    std::vector<tc::GroupMaps> maps(plan.groups.size());
+    if (precision == NA_PREC_BF16) {
+        if ((rc = tc::configure_all())) return rc;
+        for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
+            Group& g = plan.groups[gi];
+            g.maps = &maps[gi];
+            rc = tc::build_group_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.act, g.cosb, g.dz, g.dy, g.wbf16, *g.maps);
+            if (rc) return rc;
+            tc::mirror_weights(g.d_recs, g.lm, g.nf, g.wbf16, stream);
+            NA_LAUNCH_OK("mirror_weights");
+        }
+    }
+
+    // ---- epoch loop
+    auto record_epoch = [&](cudaStream_t main, std::vector<cudaStream_t>& side, cudaEvent_t fork,
+                            std::vector<cudaEvent_t>& joins) -> int {
+        const bool parallel = !side.empty();
+        if (parallel) cudaEventRecord(fork, main);
+        for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
+            cudaStream_t s = parallel ? side[gi] : main;
+            if (parallel) cudaStreamWaitEvent(s, fork, 0);
+            const Group& g = plan.groups[gi];
+            if (precision == NA_PREC_FP32) fp32_epoch(g, plan, beta1, beta2, eps, s);
+            else {
+                int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
+                                   g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
+                                   g.losspart_per_fit, g.mtiles, s);
+                if (r2) return r2;
+                launch_adam(g, plan, beta1, beta2, eps, s);
+            }
+            if (parallel) { cudaEventRecord(joins[gi], s); cudaStreamWaitEvent(main, joins[gi], 0); }
+        }
+        f32::tick_kernel<<<1, 32, 0, main>>>(plan.d_epoch);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("epoch launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
+        return NA_OK;
+    };
+
+    if (epochs > 0) {
+        const bool use_graph = !env_flag("NERFATTN_NO_GRAPH");
+        if (use_graph) {
+            cudaStream_t cap;
+            NA_CUDA_OK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+            std::vector<cudaStream_t> side(plan.groups.size() > 1 ? plan.groups.size() : 0);
+            std::vector<cudaEvent_t> joins(side.size());
+            cudaEvent_t fork = nullptr;
+            for (auto& s : side) NA_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            for (auto& e : joins) NA_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            NA_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            NA_CUDA_OK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+            rc = record_epoch(cap, side, fork, joins);
+            cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+            if (rc == NA_OK && ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
+            if (rc == NA_OK) {
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
+            }
+            for (int e = 0; rc == NA_OK && e < epochs; ++e) {
+                ce = cudaGraphLaunch(exec, stream);
+                if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
+            }
+            if (exec && rc == NA_OK) park_graph(exec, graph, stream);
+            else { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); }
+            for (auto& s : side) cudaStreamDestroy(s);
+            for (auto& e : joins) cudaEventDestroy(e);
+            cudaEventDestroy(fork);
+            cudaStreamDestroy(cap);
+            if (rc) return rc;
+        } else {
+            std::vector<cudaStream_t> none; std::vector<cudaEvent_t> nonej;
+            for (int e = 0; e < epochs; ++e) {
+                rc = record_epoch(stream, none, nullptr, nonej);
+                if (rc) return rc;
+            }
+        }
+    }
+    // ---- final metrics
+    for (Group& g : plan.groups) {
+        final_eval(g, precision, stream);
+        NA_LAUNCH_OK("final_eval");
+    }
+    return NA_OK;
+}
+
+// =========================================================================== forward / decode
+namespace na {
+
+// common set-up of the inference entries: one shape for all models
+struct InferPlan {
+    Group g;
+    float** d_out;        // device array of per-model output pointers
+    float* u; float* c0;  // decode: folded query
+    float* dotpart; int nparts;
+    size_t bytes;
+};
+
+static int infer_validate(const na_fit_t* m, int n, bool need_stats) {
+    if (!m || n <= 0) { set_error("models must be a non-empty array"); return NA_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (m[i].N != m[0].N || m[i].D != m[0].D || m[i].H != m[0].H || m[i].L != m[0].L) {
+            set_error("model %d: all models of one call must share (N, D, H, L)", i); return NA_ERR_UNSUPPORTED;
+        }
+        if (m[i].N < 1 || m[i].H % 4 || m[i].D % 4 || m[i].L < 0 || m[i].L > kMaxHidden) { set_error("model %d: unsupported shape", i); return NA_ERR_UNSUPPORTED; }
+        if (!m[i].positions || !m[i].params || (need_stats && (!m[i].mean || !m[i].std))) { set_error("model %d: null pointer", i); return NA_ERR_INVALID; }
+    }
+    return NA_OK;
+}
+
+static void infer_plan(const na_fit_t* m, int n, int precision, bool decode, void* ws, InferPlan& p) {
+    Arena ar(ws);
+    Group& g = p.g;
+    g = Group{};
+    g.N = m[0].N; g.D = m[0].D; g.H = m[0].H; g.L = m[0].L; g.nf = n;
+    g.lm = make_layer_map(g.H, g.L, g.D);
+    g.mtiles = ceil_div(g.N, 128);
+    g.d_recs = ar.take<FitRec>(n);
+    p.d_out = ar.take<float*>(n);
+    const bool bf = precision == NA_PREC_BF16;
+    const size_t nh = (size_t)n * g.N * g.H;
+    g.act[0] = ar.take<char>(nh * (bf ? 2 : 4));
+    g.act[1] = ar.take<char>(nh * (bf ? 2 : 4));
+    g.wbf16 = bf ? ar.take<__nv_bfloat16>((size_t)n * g.lm.P) : nullptr;
+    p.u = p.c0 = p.dotpart = nullptr; p.nparts = 0;
+    if (decode) {
+        p.u = ar.take<float>((size_t)n * g.H);
+        p.c0 = ar.take<float>(n);
+        p.nparts = bf ? (g.H / tc::hidden_bn(g.H)) * 2 : ceil_div(g.H, f32::BN);
+        p.dotpart = ar.take<float>((size_t)n * p.nparts * g.N);
+    }
+    p.bytes = ar.bytes();
+}
+
+static int infer_upload(const na_fit_t* m, int n, const InferPlan& p, float* const* outs, cudaStream_t stream) {
+    std::vector<FitRec> recs(n);
+    for (int i = 0; i < n; ++i) {
+        FitRec& r = recs[i];
+        memset(&r, 0, sizeof(r));
+        r.pos = m[i].positions; r.params = m[i].params; r.omega = m[i].omega0;
+        r.mean = m[i].mean; r.stdv = m[i].std;
+    }
+    NA_CUDA_OK(cudaMemcpyAsync(p.g.d_recs, recs.data(), n * sizeof(FitRec), cudaMemcpyHostToDevice, stream));
+    NA_CUDA_OK(cudaMemcpyAsync(p.d_out, outs, n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    return NA_OK;
+}
+
+}  // namespace na
+
+extern "C" int nerfattn_forward_workspace_bytes(const na_fit_t* models, int32_t n, size_t* bytes) {
+    if (!bytes) { set_error("bytes is null"); return NA_ERR_INVALID; }
+    int rc = infer_validate(models, n, false);
+    if (rc) return rc;
+    InferPlan p; infer_plan(models, n, NA_PREC_FP32, false, nullptr, p);
+    *bytes = p.bytes;
+    return NA_OK;
+}
+
+extern "C" int nerfattn_siren_forward(const na_fit_t* models, int32_t n, int32_t denormalise, float* const* out,
+                                      void* workspace, size_t workspace_bytes, na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = infer_validate(models, n, denormalise != 0);
+    if (rc) return rc;
+    if (!out) { set_error("out is null"); return NA_ERR_INVALID; }
+    if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return NA_ERR_WORKSPACE; }
+    InferPlan p; infer_plan(models, n, NA_PREC_FP32, false, workspace, p);
+    if (p.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", p.bytes, workspace_bytes); return NA_ERR_WORKSPACE; }
+    if ((rc = infer_upload(models, n, p, out, stream))) return rc;
+    const Group& g = p.g;
+    float* act[kMaxHidden + 1];
+    for (int l = 0; l <= g.L; ++l) act[l] = (float*)g.act[l & 1];
+    fp32_forward_hidden(g, act, nullptr, g.L, stream);
+    fp32_output_layer(g, act[g.L], true, stream, p.d_out, denormalise);
+    NA_LAUNCH_OK("siren_forward");
+    return NA_OK;
+}
+
+extern "C" int nerfattn_decode_workspace_bytes(const na_fit_t* models, int32_t n, int32_t precision, size_t* bytes) {
+    if (!bytes) { set_error("bytes is null"); return NA_ERR_INVALID; }
+    int rc = infer_validate(models, n, true);
+    if (rc) return rc;
+    if (precision != NA_PREC_FP32 && precision != NA_PREC_BF16) { set_error("precision %d not implemented", precision); return NA_ERR_UNSUPPORTED; }
+    InferPlan p; infer_plan(models, n, precision, true, nullptr, p);
+    *bytes = p.bytes;
+    return NA_OK;
+}
+
+extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void* q_fp16, float* const* scores,
+                                  int32_t precision, int32_t reuse_setup, void* workspace, size_t workspace_bytes,
+                                  na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = infer_validate(models, n, true);
+    if (rc) return rc;
+    if (precision != NA_PREC_FP32 && precision != NA_PREC_BF16) { set_error("precision %d not implemented", precision); return NA_ERR_UNSUPPORTED; }
+    if (!q_fp16 || !scores) { set_error("null q / scores"); return NA_ERR_INVALID; }
+    if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return NA_ERR_WORKSPACE; }
+    const bool bf = precision == NA_PREC_BF16;
+    if (bf && (!tc::shape_supported(models[0].N, 128, models[0].H, models[0].L))) {
+        set_error("bf16 decode needs N %% 128 == 0 and H in {64,128,256,512}"); return NA_ERR_UNSUPPORTED;
+    }
+    InferPlan p; infer_plan(models, n, precision, true, workspace, p);
+    if (p.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", p.bytes, workspace_bytes); return NA_ERR_WORKSPACE; }
+    const Group& g = p.g;
+    const size_t nh = (size_t)g.N * g.H;
+    if (bf && (rc = tc::configure_all())) return rc;
+    if (!reuse_setup) {
+        if ((rc = infer_upload(models, n, p, scores, stream))) return rc;
+        if (bf) { tc::mirror_weights(g.d_recs, g.lm, n, g.wbf16, stream); NA_LAUNCH_OK("mirror_weights"); }
+    }
+    dec::decode_prep_kernel<<<n, 256, 0, stream>>>(g.d_recs, (const __half*)q_fp16, g.D, g.H, g.lm.w_off[g.L + 1],
+                                                   g.lm.b_off[g.L + 1], p.u, p.c0);
+    NA_LAUNCH_OK("decode_prep_kernel");
+    if (g.L == 0) {
+        dec::l0dot_kernel<<<dim3(ceil_div(g.N, 8), n), 256, 0, stream>>>(g.d_recs, g.N, g.H, p.u, p.c0, p.d_out);
+        NA_LAUNCH_OK("l0dot_kernel");
+        return NA_OK;
+    }
+    if (!bf) {
+        float* act[kMaxHidden + 1];
+        for (int l = 0; l <= g.L; ++l) act[l] = (float*)g.act[l & 1];
+        fp32_forward_hidden(g, act, nullptr, g.L - 1, stream);
+        f32::GemmArgs a; base_args(a, g);
+        a.M = g.N; a.N = g.H; a.K = g.H;
+        a.A = act[g.L - 1]; a.a_fit = nh; a.lda = g.H;
+        a.b_param_off = g.lm.w_off[g.L]; a.ldb = g.H;
+        a.bias_off = g.lm.b_off[g.L];
+        a.dotvec = p.u; a.dotvec_fit = g.H;
+        a.dotpart = p.dotpart; a.dotpart_fit = (size_t)p.nparts * g.N;
+        launch_sgemm<f32::kFwdDot, true, true>(a, n, 1, stream);
+    } else {
+        const int bn = tc::hidden_bn(g.H);
+        {
+            const size_t total4 = nh / 4;
+            dim3 grid((unsigned)ceil_div(total4, (size_t)256), n);
+            f32::layer0_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(g.d_recs, g.N, g.H, (__nv_bfloat16*)g.act[0], nullptr, nh);
+        }
+        tc::TcArgs base{};
+        base.nb = n; base.recs = g.d_recs;
+        for (int l = 1; l <= g.L; ++l) {
+            tc::GemmMaps maps;
+            if ((rc = tc::make_operand_map(&maps.a, g.act[(l - 1) & 1], g.N, g.H, n, nh, false, tc::BM))) return rc;
+            if ((rc = tc::make_operand_map(&maps.b, g.wbf16 + g.lm.w_off[l], g.H, g.H, n, g.lm.P, false, bn))) return rc;
+            tc::TcArgs a = base;
+            a.M = g.N; a.N = g.H; a.K = g.H; a.bias_off = g.lm.b_off[l];
+            if (l < g.L) {
+                a.out0 = (__nv_bfloat16*)g.act[l & 1]; a.out0_fit = nh; a.out1 = nullptr;
+                if ((rc = tc::launch_bn<tc::kFwdSine, false, false>(bn, maps, a, stream))) return rc;
+            } else {
+                a.dotvec = p.u; a.dotvec_fit = g.H;
+                a.dotpart = p.dotpart; a.dotpart_fit = (size_t)p.nparts * g.N;
+                if ((rc = tc::launch_bn<tc::kFwdDot, false, false>(bn, maps, a, stream))) return rc;
+            }
+        }
+    }
+    dec::decode_finish_kernel<<<dim3(ceil_div(g.N, 256), n), 256, 0, stream>>>(p.dotpart, p.nparts, g.N, p.c0, p.d_out);
+    NA_LAUNCH_OK("decode");
+    return NA_OK;
+}
+
+extern "C" int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float* scores, int32_t n, int32_t N,
+                                  int32_t D, na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!k_fp16 || !q_fp16 || !scores || n <= 0 || N <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    if (D != 64 && D != 128 && D != 256) { set_error("kvread: D must be 64, 128 or 256"); return NA_ERR_UNSUPPORTED; }
+    const long long rows = (long long)n * N;
+    const int G = D / 8;
+    const long long groups_needed = (rows + 3) / 4;
+    long long blocks = (groups_needed * G + 255) / 256;
+    const long long cap = (long long)tc::num_sms() * 8;         // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const uint4* K = (const uint4*)k_fp16; const uint4* q = (const uint4*)q_fp16;
+    if (G == 8) dec::kvread_qk_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
+    else if (G == 16) dec::kvread_qk_kernel<16><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
+    else dec::kvread_qk_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
+    NA_LAUNCH_OK("kvread_qk_kernel");
+    return NA_OK;
+}
+
+extern "C" int nerfattn_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, float* c, int32_t M, int32_t N,
+                                        int32_t K, int32_t batch, int32_t a_mn, int32_t b_mn, na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a_bf16 || !b_bf16 || !c || M <= 0 || batch <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    if (N % 64 || K % 64 || N <= 0 || K <= 0 || (a_mn && M % 8)) { set_error("debug gemm: N and K must be multiples of 64"); return NA_ERR_UNSUPPORTED; }
+    int rc = tc::configure_all();
+    if (rc) return rc;
+    const int bn = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+    tc::GemmMaps maps;
+    if (a_mn) rc = tc::make_operand_map(&maps.a, a_bf16, K, M, batch, (size_t)K * M, true, 0);
+    else rc = tc::make_operand_map(&maps.a, a_bf16, M, K, batch, (size_t)M * K, false, tc::BM);
+    if (rc) return rc;
+    if (b_mn) rc = tc::make_operand_map(&maps.b, b_bf16, K, N, batch, (size_t)K * N, true, 0);
+    else rc = tc::make_operand_map(&maps.b, b_bf16, N, K, batch, (size_t)N * K, false, bn);
+    if (rc) return rc;
+    tc::TcArgs a{};
+    a.M = M; a.N = N; a.K = K; a.nb = batch;
+    a.fout = c; a.fout_fit = (size_t)M * N; a.fout_off = 0; a.ldf = N;
+    if (!a_mn && !b_mn) return tc::launch_bn<tc::kRaw, false, false>(bn, maps, a, stream);
+    if (!a_mn && b_mn) return tc::launch_bn<tc::kRaw, false, true>(bn, maps, a, stream);
+    if (a_mn && !b_mn) return tc::launch_bn<tc::kRaw, true, false>(bn, maps, a, stream);
+    return tc::launch_bn<tc::kRaw, true, true>(bn, maps, a, stream);
+}
