@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Headline benchmark: SIREN fit-epochs/s over the 280-fit sweep (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, one JSON line
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A *step* is one full pass of the hot path over the workload: all 280 fits of the
+sweep (5 layers x 4 KV heads x key/value x 7 architectures, synthetic Llama-3.1-8B
+shaped KV, N=2048, D=128) trained for `--epochs` (default 2000) full-batch Adam
+steps and evaluated.  `value` = fits x epochs x steps x N_gpus / device time of the
+K timed steps with inputs resident in HBM; `e2e` is the same through the public
+API (`fit_many`) from pinned host tensors with results read back, every step.
+Multi-GPU: weak scaling -- every rank runs a 280-fit sweep on its own layers, no
+collective on the hot path, one all-gather of the final metrics per step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT / 'nerf-attention_b200', ROOT):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+METRIC = 'siren_fit_epochs_per_sec_280fit_sweep'
+UNIT = 'fit-epochs/s'
+SWEEP_LAYERS = [0, 8, 16, 24, 31]       # reference fit.py:44-45 for 32 layers
+SWEEP_HEADS = 4
+NUM_LAYERS, NUM_KV_HEADS, HEAD_DIM = 32, 8, 128
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', choices=['native', 'reference'], default='native')
+    ap.add_argument('--precision', choices=['bf16', 'fp32'], default='bf16')
+    ap.add_argument('--epochs', type=int, default=2000)
+    ap.add_argument('--seq_len', type=int, default=2048)
+    ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end and CPU legs (profiling runs)')
+    ap.add_argument('--cpu-epochs', type=int, default=40, help='epochs per architecture in the CPU sample')
+    return ap.parse_args()
+
+
+def world():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+def sweep_tensors(rank: int, seq_len: int):
+    """Synthetic KV tensors of this rank's sweep: rank r shifts the 5 layers by r (weak scaling)."""
+    from nerf_attention.extract import synthetic_head
+    out = {}
+    for base in SWEEP_LAYERS:
+        layer = (base + rank) % NUM_LAYERS
+        for head in range(SWEEP_HEADS):
+            out[(layer, head)] = synthetic_head(layer, head, seq_len, NUM_LAYERS, NUM_KV_HEADS, HEAD_DIM)
+    return out
+
+
+def sweep_jobs(tensors, pin: bool):
+    """280 FitJobs in the reference loop order (fit.py:54-65) with the SURVEY 8d seed convention."""
+    import nerf_attention as na
+    jobs, meta = [], []
+    for (layer, head), (keys, values) in sorted(tensors.items()):
+        for is_value, tensor in ((0, keys), (1, values)):
+            t = tensor.pin_memory() if pin else tensor
+            for ci, cfg in enumerate(na.CONFIGS_FULL):
+                torch.manual_seed(1000 * layer + 100 * head + 10 * is_value + ci)
+                jobs.append(na.FitJob(t, cfg, na.SIREN(cfg, out_features=HEAD_DIM),
+                                      f"L{layer}_H{head}_{'value' if is_value else 'key'}_{cfg.name}"))
+                meta.append((layer, head, is_value, ci))
+    return jobs, meta
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[5:9]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        busy = [c for c, p in zip(sm, power) if p > 300] or sm
+        return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peaks() -> dict:
+    path = ROOT / 'MEASURED_PEAKS.json'
+    if path.exists():
+        d = json.loads(path.read_text())
+        return {'bf16_burst': d.get('bf16_tflops'), 'bf16_sustained': d.get('bf16_tflops_sustained'),
+                'hbm_gbs': d.get('hbm_gbs'), 'source': 'MEASURED_PEAKS.json'}
+    return {'bf16_burst': 1590.0, 'bf16_sustained': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+# ----------------------------------------------------------------------------- CPU / reference legs
+def cpu_sample(seq_len: int, epochs: int, warm: int = 3) -> dict:
+    """The reference's CPU path (oracle port of fit_siren) on this box's host cores: each of the 7
+    architectures on one synthetic key tensor for `epochs` epochs -- the sweep's own mix (equal
+    fits per architecture), so 7*epochs / seconds is the sweep's fit-epochs/s on the CPU."""
+    from nerf_attention.extract import synthetic_head
+    from nerf_attention.types import CONFIGS_FULL
+    from oracle import siren_oracle as orc
+    kv, _ = synthetic_head(16, 0, seq_len, NUM_LAYERS, NUM_KV_HEADS, HEAD_DIM)
+    per_cfg, total = {}, 0.0
+    for ci, cfg in enumerate(CONFIGS_FULL):
+        torch.manual_seed(16000 + ci)
+        state = orc.init_state(cfg.hidden_features, cfg.hidden_layers, cfg.omega_0, HEAD_DIM)
+        orc.fit(kv, cfg.hidden_features, cfg.hidden_layers, cfg.omega_0, epochs=warm, device='cpu',
+                log_every=10 ** 9, init=state)
+        t0 = time.perf_counter()
+        orc.fit(kv, cfg.hidden_features, cfg.hidden_layers, cfg.omega_0, epochs=epochs, device='cpu',
+                log_every=10 ** 9, init=state)
+        dt = time.perf_counter() - t0
+        per_cfg[cfg.name] = epochs / dt
+        total += dt
+    return {'value': 7 * epochs / total, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'host_cpus': os.cpu_count(), 'seconds': total, 'epochs_per_sec_by_arch': per_cfg,
+            'sample': f'oracle port of reference fit_siren (torch CPU, {torch.get_num_threads()} threads): 7 architectures x '
+                      f'1 synthetic key tensor [{seq_len}x{HEAD_DIM}] x {epochs} epochs after {warm} warm-up epochs'}
+
+
+def run_reference(args) -> None:
+    rank, _, _ = world()
+    if rank != 0:
+        return
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_sample(args.seq_len, max(2, args.cpu_epochs // 8), warm=1)
+    vals, secs, last = [], [], None
+    for _ in range(max(args.steps, 1)):
+        last = cpu_sample(args.seq_len, args.cpu_epochs)
+        vals.append(last['value']); secs.append(last['seconds'])
+    value = 7 * args.cpu_epochs * len(vals) / sum(secs)
+    last['value'] = value
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(secs) / len(secs),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 'fp32'),
+        'cpu_baseline': last,
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+def workload_config(args, precision: str) -> dict:
+    return {'workload': f'sweep280: layers {SWEEP_LAYERS} x {SWEEP_HEADS} KV heads x key/value x 7 architectures '
+                        f'(CONFIGS_FULL), synthetic Llama-3.1-8B-shaped KV [N={args.seq_len}, D={HEAD_DIM}], '
+                        f'{args.epochs} epochs per fit; one step = the whole sweep',
+            'fits_per_gpu': 280, 'epochs': args.epochs, 'seq_len': args.seq_len, 'head_dim': HEAD_DIM,
+            'precision': precision, 'parallelism': f'fits sharded by (layer, head): {args.gpus} x 280 fits',
+            'l2': 'per-step working set (activations + targets) is several GB >> 126 MB L2; no flush needed'}
+
+
+def torch_eager_on_gpu(seq_len: int, epochs: int = 60) -> dict:
+    """The reference's own torch-eager path on this B200 (oracle port, device='cuda'), medium config."""
+    from nerf_attention.extract import synthetic_head
+    from oracle import siren_oracle as orc
+    kv, _ = synthetic_head(16, 0, seq_len, NUM_LAYERS, NUM_KV_HEADS, HEAD_DIM)
+    torch.manual_seed(1)
+    state = orc.init_state(256, 2, 30.0, HEAD_DIM)
+    orc.fit(kv, 256, 2, 30.0, epochs=10, device='cuda', log_every=10 ** 9, init=state)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    orc.fit(kv, 256, 2, 30.0, epochs=epochs, device='cuda', log_every=10 ** 9, init=state)
+    torch.cuda.synchronize()
+    return {'medium_epochs_per_sec': epochs / (time.perf_counter() - t0),
+            'sample': f'oracle port on cuda, medium, [{seq_len}x{HEAD_DIM}], {epochs} epochs, one fit at a time'}
+
+
+# ----------------------------------------------------------------------------- native arm
+def run_native(args) -> None:
+    import torch.distributed as dist
+    import nerf_attention as na
+    from nerf_attention import _native, batched
+    from nerf_attention.sharding import gather_rows
+
+    rank, local_rank, wsize = world()
+    assert torch.cuda.is_available(), 'bench.py needs a B200; there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if wsize > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=wsize, device_id=dev)
+    _native.lib()                                            # fail loudly before any timing
+
+    tensors = sweep_tensors(rank, args.seq_len)
+    jobs, meta = sweep_jobs(tensors, pin=True)
+    total_flops = sum(j.config.flops_per_epoch(args.seq_len, HEAD_DIM) for j in jobs) * args.epochs
+    fit_epochs_per_step = len(jobs) * args.epochs
+
+    def barrier():
+        if wsize > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_metrics(results) -> np.ndarray:
+        rows = np.array([[*m, r.final_cosine_mean, r.final_mse] for m, r in zip(meta, results)], dtype=np.float64)
+        return gather_rows(rows, dev)
+
+    def max_over_ranks(seconds: float) -> float:
+        if wsize == 1:
+            return seconds
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: inputs and initial weights already in HBM
+    batch = batched.FitBatch(jobs, epochs=args.epochs, device=str(dev), precision=args.precision, keep_initial=True)
+    scal_dev = batch.scal.buf
+
+    def device_step():
+        batch.reset()
+        batch.launch()
+        if wsize > 1:                                         # the sweep's one collective: final metrics
+            out = [torch.empty_like(scal_dev) for _ in range(wsize)]
+            dist.all_gather(out, scal_dev)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_seconds = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    results = batch.collect()
+    launches = batch.launches_per_call() * args.steps
+    cos_keys = float(np.mean([r.final_cosine_mean for m, r in zip(meta, results) if m[2] == 0]))
+    cos_vals = float(np.mean([r.final_cosine_mean for m, r in zip(meta, results) if m[2] == 1]))
+    del batch
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: public API, host tensors in, results out, every step
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            for j in jobs:                                    # fresh seeded models each step (host work counted)
+                j.model = None
+            k = 0
+            for (layer, head), _kv in sorted(tensors.items()):
+                for is_value in (0, 1):
+                    for ci, cfg in enumerate(na.CONFIGS_FULL):
+                        torch.manual_seed(1000 * layer + 100 * head + 10 * is_value + ci)
+                        jobs[k].model = na.SIREN(cfg, out_features=HEAD_DIM)
+                        k += 1
+            res = na.fit_many(jobs, epochs=args.epochs, device=str(dev), verbose=False, precision=args.precision)
+            gather_metrics(res)
+            return batched.last_stats
+        e2e_step()                                            # warm-up (allocator, pinned pools)
+        barrier()
+        t0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        stats = None
+        for _ in range(args.steps):
+            stats = e2e_step()
+        ev1.record()
+        barrier()
+        e2e_seconds = max_over_ranks(max(time.perf_counter() - t0, ev0.elapsed_time(ev1) / 1e3))
+        e2e = {'value': fit_epochs_per_step * args.steps * wsize / e2e_seconds, 'unit': UNIT,
+               'h2d_bytes_per_step': stats.h2d_bytes, 'd2h_bytes_per_step': stats.d2h_bytes,
+               'ms_per_step': 1e3 * e2e_seconds / args.steps,
+               'host_setup_ms_per_step': 1e3 * stats.setup_seconds,
+               'api': 'nerf_attention.fit_many(280 FitJobs from pinned host tensors) + metrics all-gather; '
+                      'includes seeded CPU model construction, H2D of tensors/weights, D2H of losses/metrics'}
+
+    if rank != 0:
+        if wsize > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    achieved = total_flops * args.steps / dev_seconds / 1e12            # per GPU: max-over-ranks time, own flops
+    if args.precision == 'bf16':
+        roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / peaks['bf16_sustained'], 'traffic': None,
+                'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a seconds-long step)",
+                'kernel': 'whole step (tc_gemm_kernel fwd/out/dX/dW + SIMT layer0/Adam): algorithmic GEMM FLOPs '
+                          '6N(LH^2+HD)+4NH per fit-epoch / step time'}
+    else:
+        fp32_peak = 148 * 128 * 2 * (clocks['sm_mhz'] or 1965.0) * 1e6 / 1e12
+        roof = {'bound': 'fp32-fma', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / fp32_peak, 'traffic': None,
+                'peak_source': '148 SM x 128 lanes x 2 x median SM clock under load',
+                'kernel': 'whole step (sgemm_kernel family)'}
+
+    line = {
+        'metric': METRIC, 'value': fit_epochs_per_step * args.steps * wsize / dev_seconds, 'unit': UNIT,
+        'n_gpus': wsize, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dev_seconds / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': workload_config(args, args.precision),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof,
+        'quality': {'cos_keys_mean': cos_keys, 'cos_values_mean': cos_vals,
+                    'note': 'final CosSim of this run; parity vs the oracle is asserted in tests/ (fp32 1e-3, bf16 5e-3)'},
+        'tflops_per_gpu': achieved,
+    }
+    if not args.no_e2e:
+        line['cpu_baseline'] = cpu_sample(args.seq_len, args.cpu_epochs)
+        try:
+            line['torch_eager_b200'] = torch_eager_on_gpu(args.seq_len)
+        except Exception as exc:                              # informational only
+            line['torch_eager_b200'] = {'error': str(exc)}
+    print(json.dumps(line))
+    if wsize > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == '__main__':
+    main()

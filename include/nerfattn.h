@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NERFATTN_ABI_VERSION 3
+#define NERFATTN_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NA_API __attribute__((visibility("default")))
@@ -118,6 +118,11 @@ NA_API int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t epo
                          int32_t first_step, int32_t precision,
                          void* workspace, size_t workspace_bytes, na_stream_t stream);
 
+/* Number of kernel launches nerfattn_fit_batched enqueues for this job list (graph replays
+ * counted once per epoch): set-up + epochs * per-epoch + final metrics. */
+NA_API long long nerfattn_fit_launch_count(const na_fit_t* fits, int32_t nfits, int32_t epochs,
+                                           int32_t precision);
+
 /*
  * Full-sequence reconstruction out[i][N,D] = SIREN_i(positions) (optionally
  * * std + mean).  Replaces model(positions) in profile_latency
@@ -142,7 +147,8 @@ NA_API int nerfattn_forward_workspace_bytes(const na_fit_t* models, int32_t n, s
  *   precision    NA_PREC_FP32 (SIMT) or NA_PREC_BF16 (tcgen05 hidden layers)
  *   reuse_setup  0: upload model table / bf16 weight mirror into the workspace, then run;
  *                1: the workspace still holds the set-up of an earlier call with the same
- *                   models (only q changed): run only -- this is the per-token cost
+ *                   models and the same score pointers (only q changed): run only -- this is
+ *                   the per-token cost; `scores` is not re-read
  * All n models must share (N, D, H, L).  Reads N, D, H, L, omega0, positions, params,
  * mean, std of each na_fit_t.
  */

@@ -356,6 +356,21 @@ extern "C" int nerfattn_fit_workspace_bytes(const na_fit_t* fits, int32_t nfits,
     return NA_OK;
 }
 
+extern "C" long long nerfattn_fit_launch_count(const na_fit_t* fits, int32_t nfits, int32_t epochs, int32_t precision) {
+    if (validate(fits, nfits, precision)) return -1;
+    Plan plan{};
+    make_plan(fits, nfits, 1, precision, nullptr, plan);
+    long long setup = (long long)plan.uniq_ptr.size() /* <= one norm launch per tensor */ + plan.groups.size();
+    long long per_epoch = 1 /* tick */, fin = 0;
+    for (const Group& g : plan.groups) {
+        // layer0 + L fwd + out + (L+1) x (dW, dX) + Adam; the tensor path adds the layer-0 gradient kernel
+        per_epoch += 1 + g.L + 1 + 2 * (g.L + 1) + 1 + (precision == NA_PREC_BF16 ? 1 : 0);
+        fin += 1 + g.L + 1 + 2;
+        if (precision == NA_PREC_BF16) setup += 1;   // bf16 weight mirror
+    }
+    return setup + per_epoch * epochs + fin;
+}
+
 extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t epochs, const double* lr_table,
                                     double beta1, double beta2, double eps, int32_t first_step,
                                     int32_t precision, void* workspace, size_t workspace_bytes,

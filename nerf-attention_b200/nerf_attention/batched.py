@@ -103,135 +103,180 @@ def adopt_packed(model: SIREN, flat: torch.Tensor) -> None:
         off += n
 
 
-def fit_many(jobs: list[FitJob], epochs: int = 5000, lr: float = 1e-4, device: str = 'cuda',
-             log_every: int = 500, verbose: bool = True, precision: str | None = None,
-             betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> list[FitResult]:
-    """Train all jobs for ``epochs`` full-batch Adam steps; one FitResult per job, in order."""
-    global last_stats
-    dev = _native.require_cuda(device)
-    lib = _native.lib()
-    prec = _native.precision_code(precision)
-    if not jobs:
-        return []
-    stats = TransferStats()
-    t_wall = time.perf_counter()
+class FitBatch:
+    """One batched fit, split into its phases so that callers (bench.py) can time them apart:
+    ``__init__`` uploads and packs (H2D), ``launch`` enqueues the native call, ``reset`` restores
+    the initial weights / zero Adam moments on the device, ``collect`` reads results back (D2H)
+    and builds the FitResults.  ``fit_many`` is ``FitBatch(...).launch().collect()``."""
 
-    # ---- models: built on the CPU in job order so a seeded run matches the reference's stream
-    for job in jobs:
-        if job.kv_tensor.dim() != 2:
-            raise ValueError(f'kv_tensor must be (seq_len, d_head), got {tuple(job.kv_tensor.shape)}')
-        if job.model is None:
-            job.model = SIREN(job.config, out_features=job.kv_tensor.shape[1])
-    n_params = [job.model.count_parameters() for job in jobs]
+    def __init__(self, jobs: list[FitJob], epochs: int = 5000, lr: float = 1e-4, device: str = 'cuda',
+                 precision: str | None = None, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 keep_initial: bool = False):
+        self.dev = dev = _native.require_cuda(device)
+        self.lib = _native.lib()
+        self.prec = _native.precision_code(precision)
+        self.jobs, self.epochs, self.betas, self.eps = jobs, epochs, betas, eps
+        self.stats = stats = TransferStats()
+        t_wall = time.perf_counter()
 
-    with torch.cuda.device(dev):
-        # ---- inputs: each distinct tensor / position vector goes up once
-        uploaded: dict[tuple, torch.Tensor] = {}
-        targets, positions = [], []
-        pos_cache: dict[int, torch.Tensor] = {}
+        # ---- models: built on the CPU in job order so a seeded run matches the reference's stream
         for job in jobs:
-            t = job.kv_tensor
-            key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), str(t.device))
-            if key not in uploaded:
-                src = t.detach()
-                if src.dtype != torch.float32:
-                    src = src.float()
-                if src.device != dev:
-                    stats.h2d_bytes += src.numel() * 4
-                uploaded[key] = src.to(dev, non_blocking=True).contiguous()
-            targets.append(uploaded[key])
-            n = t.shape[0]
-            if n not in pos_cache:
-                pos_cache[n] = torch.linspace(0, 1, n).to(dev)      # CPU linspace, siren.py:82
-                stats.h2d_bytes += 4 * n
-            positions.append(pos_cache[n])
+            if job.kv_tensor.dim() != 2:
+                raise ValueError(f'kv_tensor must be (seq_len, d_head), got {tuple(job.kv_tensor.shape)}')
+            if job.model is None:
+                job.model = SIREN(job.config, out_features=job.kv_tensor.shape[1])
+        self.n_params = n_params = [job.model.count_parameters() for job in jobs]
+        self.seq = seq = [job.kv_tensor.shape[0] for job in jobs]
+        self.dh = dh = [job.kv_tensor.shape[1] for job in jobs]
 
-        # ---- packed weights: one pinned staging buffer, one copy
-        params = _Packer(n_params, dev)
-        staging = torch.empty(params.total, dtype=torch.float32, pin_memory=True)
-        for i, job in enumerate(jobs):
-            pack_model(job.model, staging[params.offsets[i]: params.offsets[i] + n_params[i]])
-        params.buf.copy_(staging, non_blocking=True)
-        stats.h2d_bytes += params.total * 4
-        adam_m = _Packer(n_params, dev, zero=True)
-        adam_v = _Packer(n_params, dev, zero=True)
+        with torch.cuda.device(dev):
+            # ---- inputs: each distinct tensor / position vector goes up once
+            uploaded: dict[tuple, torch.Tensor] = {}
+            self.targets, self.positions = [], []
+            pos_cache: dict[int, torch.Tensor] = {}
+            for job in jobs:
+                t = job.kv_tensor
+                key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), str(t.device))
+                if key not in uploaded:
+                    src = t.detach()
+                    if src.dtype != torch.float32:
+                        src = src.float()
+                    if src.device != dev:
+                        stats.h2d_bytes += src.numel() * 4
+                    uploaded[key] = src.to(dev, non_blocking=True).contiguous()
+                self.targets.append(uploaded[key])
+                n = t.shape[0]
+                if n not in pos_cache:
+                    pos_cache[n] = torch.linspace(0, 1, n).to(dev)      # CPU linspace, siren.py:82
+                    stats.h2d_bytes += 4 * n
+                self.positions.append(pos_cache[n])
 
-        seq = [job.kv_tensor.shape[0] for job in jobs]
-        dh = [job.kv_tensor.shape[1] for job in jobs]
-        losses = _Packer([epochs] * len(jobs), dev)
-        cos = _Packer(seq, dev)
-        ppm = _Packer(seq, dev)
-        scal = _Packer([8] * len(jobs), dev)
-        mean = _Packer(dh, dev)
-        std = _Packer(dh, dev)
+            # ---- packed weights: one pinned staging buffer, one copy
+            self.params = params = _Packer(n_params, dev)
+            staging = torch.empty(params.total, dtype=torch.float32, pin_memory=True)
+            for i, job in enumerate(jobs):
+                pack_model(job.model, staging[params.offsets[i]: params.offsets[i] + n_params[i]])
+            params.buf.copy_(staging, non_blocking=True)
+            stats.h2d_bytes += params.total * 4
+            self.initial = params.buf.clone() if keep_initial else None
+            self.adam_m = _Packer(n_params, dev, zero=True)
+            self.adam_v = _Packer(n_params, dev, zero=True)
+            self.losses = _Packer([epochs] * len(jobs), dev)
+            self.cos = _Packer(seq, dev)
+            self.ppm = _Packer(seq, dev)
+            self.scal = _Packer([8] * len(jobs), dev)
+            self.mean = _Packer(dh, dev)
+            self.std = _Packer(dh, dev)
 
-        fits = (_native.NaFit * len(jobs))()
-        for i, job in enumerate(jobs):
-            f = fits[i]
-            f.N, f.D = seq[i], dh[i]
-            f.H, f.L = job.config.hidden_features, job.config.hidden_layers
-            f.omega0, f.flags = job.config.omega_0, 0
-            f.positions, f.targets = positions[i].data_ptr(), targets[i].data_ptr()
-            f.mean, f.std = mean.ptr(i), std.ptr(i)
-            f.params, f.adam_m, f.adam_v = params.ptr(i), adam_m.ptr(i), adam_v.ptr(i)
-            f.losses, f.cos_sims, f.per_pos_mse, f.scalars = losses.ptr(i), cos.ptr(i), ppm.ptr(i), scal.ptr(i)
+            self.fits = fits = (_native.NaFit * len(jobs))()
+            for i, job in enumerate(jobs):
+                f = fits[i]
+                f.N, f.D = seq[i], dh[i]
+                f.H, f.L = job.config.hidden_features, job.config.hidden_layers
+                f.omega0, f.flags = job.config.omega_0, 0
+                f.positions, f.targets = self.positions[i].data_ptr(), self.targets[i].data_ptr()
+                f.mean, f.std = self.mean.ptr(i), self.std.ptr(i)
+                f.params, f.adam_m, f.adam_v = params.ptr(i), self.adam_m.ptr(i), self.adam_v.ptr(i)
+                f.losses, f.cos_sims = self.losses.ptr(i), self.cos.ptr(i)
+                f.per_pos_mse, f.scalars = self.ppm.ptr(i), self.scal.ptr(i)
 
-        need = ctypes.c_size_t(0)
-        _native.check(lib.nerfattn_fit_workspace_bytes(fits, len(jobs), prec, ctypes.byref(need)),
-                      'nerfattn_fit_workspace_bytes')
-        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
-        table = lr_schedule(epochs, lr)
+            need = ctypes.c_size_t(0)
+            _native.check(self.lib.nerfattn_fit_workspace_bytes(fits, len(jobs), self.prec, ctypes.byref(need)),
+                          'nerfattn_fit_workspace_bytes')
+            self.workspace_bytes = need.value
+            self.workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            self.table = lr_schedule(epochs, lr)
+        self.flops = [job.config.flops_per_epoch(seq[i], dh[i]) for i, job in enumerate(jobs)]
         stats.setup_seconds = time.perf_counter() - t_wall
+        self._t_wall = t_wall
 
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        _native.check(lib.nerfattn_fit_batched(
-            fits, len(jobs), epochs, table.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-            betas[0], betas[1], eps, 0, prec, workspace.data_ptr(), need.value,
-            _native.stream_handle()), 'nerfattn_fit_batched')
-        ev1.record()
+    def launch(self) -> 'FitBatch':
+        """Enqueue the whole fit on the current stream (asynchronous)."""
+        with torch.cuda.device(self.dev):
+            _native.check(self.lib.nerfattn_fit_batched(
+                self.fits, len(self.jobs), self.epochs,
+                self.table.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                self.betas[0], self.betas[1], self.eps, 0, self.prec, self.workspace.data_ptr(),
+                self.workspace_bytes, _native.stream_handle()), 'nerfattn_fit_batched')
+        return self
 
-        # ---- results back (pinned, async, one sync)
+    def reset(self) -> None:
+        """Device-side: initial weights back, Adam moments to zero (needs keep_initial=True)."""
+        self.params.buf.copy_(self.initial, non_blocking=True)
+        self.adam_m.buf.zero_()
+        self.adam_v.buf.zero_()
+
+    def launches_per_call(self) -> int:
+        return int(self.lib.nerfattn_fit_launch_count(self.fits, len(self.jobs), self.epochs, self.prec))
+
+    def collect(self, verbose: bool = False, log_every: int = 500, keep_optimizer_state: bool = False,
+                gpu_seconds: float | None = None) -> list[FitResult]:
+        """D2H of losses / metrics (pinned, async, one sync) and the FitResult records."""
+        stats, jobs, epochs = self.stats, self.jobs, self.epochs
+
         def fetch(p: _Packer) -> torch.Tensor:
             host = torch.empty(p.total, dtype=torch.float32, pin_memory=True)
             host.copy_(p.buf, non_blocking=True)
             stats.d2h_bytes += p.total * 4
             return host
-        h_losses, h_cos, h_ppm, h_scal, h_mean, h_std = (fetch(p) for p in (losses, cos, ppm, scal, mean, std))
-        torch.cuda.current_stream().synchronize()
-        stats.gpu_seconds = ev0.elapsed_time(ev1) / 1e3
-        del workspace
+        with torch.cuda.device(self.dev):
+            h_losses, h_cos, h_ppm, h_scal, h_mean, h_std = (
+                fetch(p) for p in (self.losses, self.cos, self.ppm, self.scal, self.mean, self.std))
+            torch.cuda.current_stream().synchronize()
+        if gpu_seconds is not None:
+            stats.gpu_seconds = gpu_seconds
+        total_flops = float(sum(self.flops)) or 1.0
+        results: list[FitResult] = []
+        for i, job in enumerate(jobs):
+            n, d, p = self.seq[i], self.dh[i], self.n_params[i]
+            adopt_packed(job.model, self.params.view(i, p))
+            job.model.eval()
+            if keep_optimizer_state:       # flat Adam moments in params order (tests, warm restarts)
+                job.model.adam_state = (self.adam_m.view(i, p), self.adam_v.view(i, p))
+            sc = h_scal[self.scal.offsets[i]: self.scal.offsets[i] + 8]
+            fit_losses = h_losses[self.losses.offsets[i]: self.losses.offsets[i] + epochs].tolist()
+            raw = n * d * 2                                   # fp16 KV baseline, siren.py:127
+            size = job.model.size_bytes()
+            if verbose and epochs:
+                step = max(int(log_every), 1)
+                for e in range(step, epochs + 1, step):
+                    print(f"  Epoch {e}/{epochs} | NormMSE: {fit_losses[e - 1]:.6f}")
+            results.append(FitResult(
+                model=job.model, config=job.config,
+                target_mean=h_mean[self.mean.offsets[i]: self.mean.offsets[i] + d].clone().unsqueeze(0),
+                target_std=h_std[self.std.offsets[i]: self.std.offsets[i] + d].clone().unsqueeze(0),
+                losses=fit_losses,
+                final_mse=float(sc[0]), final_cosine_mean=float(sc[1]),
+                final_cosine_min=float(sc[2]), final_cosine_std=float(sc[3]),
+                per_pos_mse=h_ppm[self.ppm.offsets[i]: self.ppm.offsets[i] + n].numpy().copy(),
+                cosine_sims=h_cos[self.cos.offsets[i]: self.cos.offsets[i] + n].numpy().copy(),
+                compression_ratio=raw / size, raw_size_bytes=raw, siren_size_bytes=size,
+                # the sweep trains concurrently: a fit's time is its FLOP share of the batch
+                train_time_seconds=stats.gpu_seconds * self.flops[i] / total_flops,
+                seq_len=n, d_head=d, num_parameters=p,
+            ))
+        stats.wall_seconds = time.perf_counter() - self._t_wall
+        return results
 
-    # ---- unpack
-    flops = [job.config.flops_per_epoch(seq[i], dh[i]) for i, job in enumerate(jobs)]
-    total_flops = float(sum(flops)) or 1.0
-    results: list[FitResult] = []
-    for i, job in enumerate(jobs):
-        adopt_packed(job.model, params.view(i, n_params[i]))
-        job.model.eval()
-        sc = h_scal[scal.offsets[i]: scal.offsets[i] + 8]
-        n, d = seq[i], dh[i]
-        fit_losses = h_losses[losses.offsets[i]: losses.offsets[i] + epochs].tolist()
-        raw = n * d * 2                                   # fp16 KV baseline, siren.py:127
-        size = job.model.size_bytes()
-        if verbose and epochs:
-            step = max(int(log_every), 1)
-            for e in range(step, epochs + 1, step):
-                print(f"  Epoch {e}/{epochs} | NormMSE: {fit_losses[e - 1]:.6f}")
-        results.append(FitResult(
-            model=job.model, config=job.config,
-            target_mean=h_mean[mean.offsets[i]: mean.offsets[i] + d].clone().unsqueeze(0),
-            target_std=h_std[std.offsets[i]: std.offsets[i] + d].clone().unsqueeze(0),
-            losses=fit_losses,
-            final_mse=float(sc[0]), final_cosine_mean=float(sc[1]),
-            final_cosine_min=float(sc[2]), final_cosine_std=float(sc[3]),
-            per_pos_mse=h_ppm[ppm.offsets[i]: ppm.offsets[i] + n].numpy().copy(),
-            cosine_sims=h_cos[cos.offsets[i]: cos.offsets[i] + n].numpy().copy(),
-            compression_ratio=raw / size, raw_size_bytes=raw, siren_size_bytes=size,
-            # the sweep trains concurrently: a fit's time is its FLOP share of the batch
-            train_time_seconds=stats.gpu_seconds * flops[i] / total_flops,
-            seq_len=n, d_head=d, num_parameters=n_params[i],
-        ))
-    stats.wall_seconds = time.perf_counter() - t_wall
-    last_stats = stats
+
+def fit_many(jobs: list[FitJob], epochs: int = 5000, lr: float = 1e-4, device: str = 'cuda',
+             log_every: int = 500, verbose: bool = True, precision: str | None = None,
+             betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+             keep_optimizer_state: bool = False) -> list[FitResult]:
+    """Train all jobs for ``epochs`` full-batch Adam steps; one FitResult per job, in order."""
+    global last_stats
+    if not jobs:
+        _native.require_cuda(device)
+        return []
+    batch = FitBatch(jobs, epochs=epochs, lr=lr, device=device, precision=precision, betas=betas, eps=eps)
+    with torch.cuda.device(batch.dev):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        batch.launch()
+        ev1.record()
+        ev1.synchronize()
+        gpu_seconds = ev0.elapsed_time(ev1) / 1e3
+    results = batch.collect(verbose=verbose, log_every=log_every, keep_optimizer_state=keep_optimizer_state,
+                            gpu_seconds=gpu_seconds)
+    last_stats = batch.stats
     return results

@@ -75,6 +75,7 @@ class PackedModels:
             f.mean, f.std = self.mean[i].data_ptr(), self.std[i].data_ptr()
         self.device = dev
         self._ws = {}
+        self._decode_out = {}
 
     def _workspace(self, kind: str, size_fn, *args) -> torch.Tensor:
         if kind not in self._ws:
@@ -99,8 +100,15 @@ class PackedModels:
         """scores [n, N] = q_i . (SIREN_i(pos) * std_i + mean_i); q fp16 [n, D]."""
         lib = _native.lib()
         prec = _native.precision_code(precision)
-        if out is None:
+        if reuse_setup:
+            # the score pointers were uploaded with the set-up: the result lands in that buffer
+            cached = self._decode_out[prec]
+            if out is not None and out.data_ptr() != cached.data_ptr():
+                raise ValueError('reuse_setup=True writes into the `out` of the set-up call; pass that tensor')
+            out = cached
+        elif out is None:
             out = torch.empty(self.n, self.seq_len, device=self.device)
+        self._decode_out[prec] = out
         ws = self._workspace(f'nerfattn_decode_workspace_bytes/{prec}', lib.nerfattn_decode_workspace_bytes, prec)
         ptrs = (ctypes.c_void_p * self.n)(*[out[i].data_ptr() for i in range(self.n)])
         assert q.dtype == torch.float16 and q.is_contiguous() and q.shape == (self.n, self.d)

@@ -1,0 +1,87 @@
+"""Decode-side kernels: SIREN-evaluated q.K (output layer folded into the query) and the
+bandwidth-bound fp16 KV-read baseline, through the C ABI, against the oracle."""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import nerf_attention as na
+from nerf_attention.evaluate import PackedModels, kvread_qk, profile_decode, profile_latency
+from nerf_attention.fit import _result_to_record, _save_model
+from oracle import siren_oracle as orc
+from gpu_util import gpu_fit, model_from_state, rel_err, seeded_state, smooth_tensor
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('n,heads,d', [(512, 3, 128), (2048, 8, 128), (300, 2, 64), (1, 1, 256)])
+def test_kvread_qk_matches_torch(cuda_device, n, heads, d):
+    g = torch.Generator(device='cuda').manual_seed(n)
+    k = torch.randn(heads, n, d, device='cuda', generator=g).half()
+    q = torch.randn(heads, d, device='cuda', generator=g).half()
+    out = kvread_qk(k, q)
+    ref = torch.stack([orc.kvread_scores(k[i].cpu(), q[i].cpu()) for i in range(heads)])
+    assert rel_err(out.cpu(), ref) <= 1e-5          # fp32 accumulate of exact fp16 products
+
+
+@pytest.mark.parametrize('name,n', [('medium', 512), ('tiny', 2048), ('large', 256), ('deep', 1024)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-5), ('bf16', 3e-2)])
+def test_decode_qk_matches_oracle(cuda_device, name, n, precision, tol):
+    cfg = next(c for c in na.CONFIGS_FULL if c.name == name)
+    heads = 3
+    states = [seeded_state(cfg, 128, 70 + i) for i in range(heads)]
+    g = torch.Generator().manual_seed(1)
+    means = [torch.randn(1, 128, generator=g) * 0.1 for _ in range(heads)]
+    stds = [torch.rand(1, 128, generator=g) + 0.5 for _ in range(heads)]
+    q = torch.randn(heads, 128, generator=g).half()
+    packed = PackedModels([model_from_state(cfg, 128, s) for s in states], n, means, stds)
+    out = packed.decode_qk(q.cuda(), precision).clone()
+    again = packed.decode_qk(q.cuda(), precision, reuse_setup=True)
+    assert torch.equal(out, again)
+    for i in range(heads):
+        ref = orc.decode_scores(states[i], cfg.omega_0, means[i], stds[i], q[i], n)
+        assert rel_err(out[i].cpu(), ref) <= tol, i
+    # a new query with the cached set-up is the per-token path
+    q2 = torch.randn(heads, 128, generator=g).half()
+    out2 = packed.decode_qk(q2.cuda(), precision, reuse_setup=True)
+    with pytest.raises(ValueError):
+        packed.decode_qk(q2.cuda(), precision, out=torch.empty_like(out2), reuse_setup=True)
+    ref2 = orc.decode_scores(states[1], cfg.omega_0, means[1], stds[1], q2[1], n)
+    assert rel_err(out2[1].cpu(), ref2) <= tol
+
+
+def test_decode_without_hidden_layers(cuda_device):
+    cfg = na.SIRENConfig(64, 0, 30.0, 'flat')
+    state = seeded_state(cfg, 128, 3)
+    q = torch.randn(1, 128).half()
+    packed = PackedModels([model_from_state(cfg, 128, state)], 200)
+    out = packed.decode_qk(q.cuda(), 'fp32')
+    ref = orc.decode_scores(state, 30.0, torch.zeros(1, 128), torch.ones(1, 128), q[0], 200)
+    assert rel_err(out[0].cpu(), ref) <= 2e-5
+
+
+def test_profile_latency_outputs(cuda_device, tmp_path):
+    cfg = na.CONFIGS_FULL[2]
+    kv = smooth_tensor(4, 512, 128)
+    res = gpu_fit(kv, cfg, 5, 'fp32', seeded_state(cfg, 128, 9))
+    rec = _result_to_record('L0_H0_key_medium', 0, 0, 'key', res)
+    _save_model(tmp_path, rec['name'], res, rec)
+    rows = profile_latency(tmp_path, tmp_path / 'fig', device='cuda')
+    saved = json.loads((tmp_path / 'fig' / 'latency_results.json').read_text())
+    assert saved == rows and len(rows) == 1
+    reference_keys = ['name', 'config', 'siren_time_ms', 'hbm_time_4060_ms', 'hbm_time_h100_ms',
+                      'speedup_vs_4060', 'speedup_vs_h100', 'num_params']
+    assert list(rows[0])[:8] == reference_keys                   # reference evaluate.py:206-215
+    assert rows[0]['num_params'] == 164992 and rows[0]['hbm_time_4060_ms'] == pytest.approx(512 * 128 * 2 / 272e9 * 1e3)
+    assert rows[0]['siren_time_ms'] > 0 and rows[0]['hbm_time_b200_measured_ms'] > 0
+
+
+def test_profile_decode_table(cuda_device):
+    cfg = na.CONFIGS_FULL[2]
+    models = [model_from_state(cfg, 128, seeded_state(cfg, 128, i)) for i in range(2)]
+    table = profile_decode(models, [512, 1024], heads_per_launch=8, warmup=2, runs=3)
+    assert [r['seq_len'] for r in table] == [512, 1024]
+    for r in table:
+        assert r['kvread_us'] > 0 and r['siren_fp32_us'] > 0 and r['siren_bf16_us'] > 0
