@@ -96,6 +96,51 @@ void set_error(const char* fmt, ...);
         }                                                                             \
     } while (0)
 
+// sin and cos of x to fp32 accuracy (<= 1.5 ulp measured for |x| <= 1000, oracle/README), with
+// no branch: 3-constant Cody-Waite reduction by pi/2 + the minimax polynomials on [-pi/4, pi/4]
+// + quadrant fix-up with integer ops.  omega_0 up to 60 puts first-layer arguments near 120, far
+// outside MUFU.SIN's accurate range, and libdevice sincosf() carries a Payne-Hanek slow path whose
+// branch stops the compiler from interleaving independent evaluations -- the sine epilogue is
+// latency-bound without that interleaving.  Callers handle |x| > kSincosFastLimit separately.
+constexpr float kSincosFastLimit = 8192.0f;
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+    float kf = fmaf(x, 0.636619772f, 12582912.0f);          // round(x * 2/pi) in the low mantissa bits
+    const int q = __float_as_int(kf);
+    kf -= 12582912.0f;
+    float r = fmaf(kf, -1.57079601e+00f, x);
+    r = fmaf(kf, -3.13916473e-07f, r);
+    r = fmaf(kf, -5.39030253e-15f, r);
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+    sp = fmaf(sp, r2, -1.66666546e-1f);
+    const float sn = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+    cp = fmaf(cp, r2, 4.16666457e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    const float cs = fmaf(cp, r2, 1.0f);
+    const bool odd = q & 1;
+    const float a = odd ? cs : sn, b = odd ? sn : cs;
+    s = __int_as_float(__float_as_int(a) ^ ((q & 2) << 30));
+    c = __int_as_float(__float_as_int(b) ^ (((q + 1) & 2) << 30));
+}
+// n evaluations, interleaved by the compiler (the loop is branch-free); rare huge arguments fall
+// back to libdevice for the whole group.
+__device__ __noinline__ float2 slow_sincos(float x) {      // out of line: keeps the hot loop small
+    float2 r;
+    sincosf(x, &r.x, &r.y);
+    return r;
+}
+template <int N>
+__device__ __forceinline__ void sincos_group(const float (&x)[N], float (&s)[N], float (&c)[N]) {
+    float big = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { fast_sincos(x[i], s[i], c[i]); big = fmaxf(big, fabsf(x[i])); }
+    if (big > kSincosFastLimit) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const float2 r = slow_sincos(x[i]); s[i] = r.x; c[i] = r.y; }   // static indices only
+    }
+}
+
 template <typename T> __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -82,7 +82,7 @@ static int validate(const na_fit_t* fits, int nfits, int precision) {
         const na_fit_t& f = fits[i];
         if (f.N < 2 || f.D < 1 || f.H < 1 || f.L < 0) { set_error("fit %d: bad shape", i); return NA_ERR_INVALID; }
         if (f.L > kMaxHidden) { set_error("fit %d: hidden_layers %d > %d", i, f.L, kMaxHidden); return NA_ERR_UNSUPPORTED; }
-        if (f.H % 4 || f.D % 4) { set_error("fit %d: H and D must be multiples of 4", i); return NA_ERR_UNSUPPORTED; }
+        if (f.H % 8 || f.D % 4) { set_error("fit %d: H must be a multiple of 8 and D a multiple of 4", i); return NA_ERR_UNSUPPORTED; }
         if (precision == NA_PREC_BF16 && !tc::shape_supported(f.N, f.D, f.H, f.L)) {
             set_error("fit %d: bf16 path needs N %% 128 == 0, H in {64,128,256,512}, D %% 64 == 0 and D <= 256 "
                       "(got N=%d D=%d H=%d)", i, f.N, f.D, f.H);
@@ -200,8 +200,8 @@ static void base_args(f32::GemmArgs& a, const Group& g) {
 static void fp32_forward_hidden(const Group& g, float* const* act, float* const* cosb, int last, cudaStream_t s) {
     const size_t nh = (size_t)g.N * g.H;
     {
-        const size_t total4 = nh / 4;
-        dim3 grid((unsigned)ceil_div(total4, (size_t)256), g.nf);
+        const size_t total8 = nh / 8;
+        dim3 grid((unsigned)ceil_div(total8, (size_t)256), g.nf);
         f32::layer0_kernel<float><<<grid, 256, 0, s>>>(g.d_recs, g.N, g.H, act[0], cosb ? cosb[0] : nullptr, nh);
     }
     for (int l = 1; l <= last; ++l) {
@@ -249,7 +249,7 @@ static void launch_adam(const Group& g, const Plan& plan, double beta1, double b
     a.loss_inv_count = 1.0f / ((float)g.N * (float)g.D);
     a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
     a.wbf16 = g.wbf16; a.wbf16_fit = g.lm.P;
-    dim3 grid(ceil_div(g.lm.P, 256), g.nf);
+    dim3 grid(ceil_div(g.lm.P, 1024), g.nf);
     f32::adam_kernel<<<grid, 256, 0, s>>>(a);
 }
 
@@ -575,7 +575,7 @@ static int infer_validate(const na_fit_t* m, int n, bool need_stats) {
         if (m[i].N != m[0].N || m[i].D != m[0].D || m[i].H != m[0].H || m[i].L != m[0].L) {
             set_error("model %d: all models of one call must share (N, D, H, L)", i); return NA_ERR_UNSUPPORTED;
         }
-        if (m[i].N < 1 || m[i].H % 4 || m[i].D % 4 || m[i].L < 0 || m[i].L > kMaxHidden) { set_error("model %d: unsupported shape", i); return NA_ERR_UNSUPPORTED; }
+        if (m[i].N < 1 || m[i].H % 8 || m[i].D % 4 || m[i].L < 0 || m[i].L > kMaxHidden) { set_error("model %d: unsupported shape", i); return NA_ERR_UNSUPPORTED; }
         if (!m[i].positions || !m[i].params || (need_stats && (!m[i].mean || !m[i].std))) { set_error("model %d: null pointer", i); return NA_ERR_INVALID; }
     }
     return NA_OK;
@@ -703,8 +703,8 @@ extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void*
     } else {
         const int bn = tc::hidden_bn(g.H);
         {
-            const size_t total4 = nh / 4;
-            dim3 grid((unsigned)ceil_div(total4, (size_t)256), n);
+            const size_t total8 = nh / 8;
+            dim3 grid((unsigned)ceil_div(total8, (size_t)256), n);
             f32::layer0_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(g.d_recs, g.N, g.H, (__nv_bfloat16*)g.act[0], nullptr, nh);
         }
         tc::TcArgs base{};

@@ -178,9 +178,10 @@ sgemm_kernel(const GemmArgs g) {
                 if (MODE == kFwdSine) {
                     const float4 bb = ldg4(rec.params + g.bias_off + n);
                     const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-                    float s[4], c[4];
+                    float s[4], c[4], arg[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sincosf(rec.omega * (r[j] + bv[j]), &s[j], &c[j]);
+                    for (int j = 0; j < 4; ++j) arg[j] = rec.omega * (r[j] + bv[j]);
+                    sincos_group(arg, s, c);
                     const size_t o = (size_t)m * g.N + n;
                     *reinterpret_cast<float4*>(g.out0 + (size_t)f * g.out0_fit + o) = make_float4(s[0], s[1], s[2], s[3]);
                     if (g.out1)
@@ -189,8 +190,12 @@ sgemm_kernel(const GemmArgs g) {
                     const float4 bb = ldg4(rec.params + g.bias_off + n);
                     const float4 uu = ldg4(g.dotvec + (size_t)f * g.dotvec_fit + n);
                     const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, uv[4] = {uu.x, uu.y, uu.z, uu.w};
+                    float s[4], c[4], arg[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) rowdot[i] = fmaf(uv[j], sinf(rec.omega * (r[j] + bv[j])), rowdot[i]);
+                    for (int j = 0; j < 4; ++j) arg[j] = rec.omega * (r[j] + bv[j]);
+                    sincos_group(arg, s, c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rowdot[i] = fmaf(uv[j], s[j], rowdot[i]);
                 } else if (MODE == kFwdOut || MODE == kFwdEval) {
                     const float4 bb = ldg4(rec.params + g.bias_off + n);
                     const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
@@ -351,29 +356,31 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 layer0_kernel(const FitRec* recs, int N, int H, OutT* act, OutT* cosb, size_t fit_stride) {
     const FitRec& rec = recs[blockIdx.y];
-    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total4 = (size_t)N * H / 4;
-    if (i4 >= total4) return;
-    const int n = (int)(i4 * 4 / H), j = (int)(i4 * 4 % H);
+    const size_t i8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // 8 consecutive features of one row
+    const size_t total8 = (size_t)N * H / 8;
+    if (i8 >= total8) return;
+    const int n = (int)(i8 * 8 / H), j = (int)(i8 * 8 % H);
     const float x = __ldg(rec.pos + n);
-    const float4 w = ldg4(rec.params + j);
-    const float4 b = ldg4(rec.params + H + j);
-    const float wv[4] = {w.x, w.y, w.z, w.w}, bv[4] = {b.x, b.y, b.z, b.w};
-    float s[4], c[4];
+    const float4 w0 = ldg4(rec.params + j), w1 = ldg4(rec.params + j + 4);
+    const float4 b0 = ldg4(rec.params + H + j), b1 = ldg4(rec.params + H + j + 4);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float arg[8], s[8], c[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sincosf(rec.omega * fmaf(x, wv[k], bv[k]), &s[k], &c[k]);
-    const size_t o = (size_t)blockIdx.y * fit_stride + i4 * 4;
+    for (int k = 0; k < 8; ++k) arg[k] = rec.omega * fmaf(x, wv[k], bv[k]);
+    sincos_group(arg, s, c);
+    const size_t o = (size_t)blockIdx.y * fit_stride + i8 * 8;
     if constexpr (sizeof(OutT) == 4) {
         *reinterpret_cast<float4*>(act + o) = make_float4(s[0], s[1], s[2], s[3]);
-        if (cosb) *reinterpret_cast<float4*>(cosb + o) = make_float4(c[0], c[1], c[2], c[3]);
+        *reinterpret_cast<float4*>(act + o + 4) = make_float4(s[4], s[5], s[6], s[7]);
+        if (cosb) {
+            *reinterpret_cast<float4*>(cosb + o) = make_float4(c[0], c[1], c[2], c[3]);
+            *reinterpret_cast<float4*>(cosb + o + 4) = make_float4(c[4], c[5], c[6], c[7]);
+        }
     } else {
-        __nv_bfloat162 s01 = __floats2bfloat162_rn(s[0], s[1]), s23 = __floats2bfloat162_rn(s[2], s[3]);
-        __nv_bfloat162 c01 = __floats2bfloat162_rn(c[0], c[1]), c23 = __floats2bfloat162_rn(c[2], c[3]);
-        uint2 sv, cv;
-        sv.x = *reinterpret_cast<uint32_t*>(&s01); sv.y = *reinterpret_cast<uint32_t*>(&s23);
-        cv.x = *reinterpret_cast<uint32_t*>(&c01); cv.y = *reinterpret_cast<uint32_t*>(&c23);
-        *reinterpret_cast<uint2*>(act + o) = sv;
-        if (cosb) *reinterpret_cast<uint2*>(cosb + o) = cv;
+        auto pk = [](float a, float b) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); };
+        *reinterpret_cast<uint4*>(act + o) = make_uint4(pk(s[0], s[1]), pk(s[2], s[3]), pk(s[4], s[5]), pk(s[6], s[7]));
+        if (cosb) *reinterpret_cast<uint4*>(cosb + o) = make_uint4(pk(c[0], c[1]), pk(c[2], c[3]), pk(c[4], c[5]), pk(c[6], c[7]));
     }
 }
 
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     const int f = blockIdx.y;
     const FitRec& rec = a.recs[f];
     const int e = *a.et.epoch;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * 4;      // 4 consecutive parameters (all regions are 4-aligned)
 
     if (blockIdx.x == 0 && threadIdx.x == 0) {          // siren.py:105  losses.append(loss.item())
         float s = 0.f;
@@ -417,26 +424,44 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     const bool is_bias = p >= a.lm.b_off[layer];
     const int width = a.lm.out_dim[layer];
 
-    float gsum = 0.f;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (is_bias || layer == 0) {
         const int j = is_bias ? p - a.lm.b_off[layer] : p;
         const int mt = is_bias ? a.col_mt[layer] : a.col_mt[0];
-        const float* src = (is_bias ? a.colpart + a.colpart_layer_off[layer] : a.xpart) +
-                           (size_t)f * mt * width + j;
-        for (int t = 0; t < mt; ++t) gsum += src[(size_t)t * width];
+        const float* src = (is_bias ? a.colpart + a.colpart_layer_off[layer] : a.xpart) + (size_t)f * mt * width + j;
+        for (int t = 0; t < mt; ++t) {
+            const float4 v = ldg4(src + (size_t)t * width);
+            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+        }
     } else {
         const float* src = a.gradpart + (size_t)f * a.grad_fit + p;
-        for (int s = 0; s < a.nsplit; ++s) gsum += src[(size_t)s * a.grad_split_stride];
+        for (int s = 0; s < a.nsplit; ++s) {
+            const float4 v = ldg4(src + (size_t)s * a.grad_split_stride);
+            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+        }
     }
 
     // torch _single_tensor_adam: lerp, mul+addcmul, sqrt/bc2_sqrt + eps, addcdiv(value=-step_size)
-    float m = rec.m[p], v = rec.v[p], w = rec.params[p];
-    m = __fadd_rn(m, __fmul_rn(1.0f - a.beta1, __fsub_rn(gsum, m)));
-    v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(1.0f - a.beta2, gsum), gsum));
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.et.bc2_sqrt[e]), a.eps);
-    w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-a.et.step_size[e], m), denom));
-    rec.m[p] = m; rec.v[p] = v; rec.params[p] = w;
-    if (a.wbf16 && layer >= 1 && !is_bias) a.wbf16[(size_t)f * a.wbf16_fit + p] = __float2bfloat16_rn(w);
+    const float4 m4 = *reinterpret_cast<const float4*>(rec.m + p), v4 = *reinterpret_cast<const float4*>(rec.v + p);
+    const float4 w4 = *reinterpret_cast<const float4*>(rec.params + p);
+    const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+    float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float bc2 = a.et.bc2_sqrt[e], nss = -a.et.step_size[e];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = __fadd_rn(m[i], __fmul_rn(1.0f - a.beta1, __fsub_rn(gs[i], m[i])));
+        v[i] = __fadd_rn(__fmul_rn(v[i], a.beta2), __fmul_rn(__fmul_rn(1.0f - a.beta2, gs[i]), gs[i]));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v[i]), bc2), a.eps);
+        w[i] = __fadd_rn(w[i], __fdiv_rn(__fmul_rn(nss, m[i]), denom));
+    }
+    *reinterpret_cast<float4*>(rec.m + p) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(rec.v + p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(rec.params + p) = make_float4(w[0], w[1], w[2], w[3]);
+    if (a.wbf16 && layer >= 1 && !is_bias) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
+        *reinterpret_cast<uint2*>(a.wbf16 + (size_t)f * a.wbf16_fit + p) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
 }
 
 __global__ void tick_kernel(int* epoch) { if (threadIdx.x == 0) *epoch += 1; }

@@ -285,16 +285,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const FitRec* rec = g.recs ? &g.recs[b] : nullptr;
             const int row = mt * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
+            const int col_base = nt * BN + half * (BN / 2);
             float sq = 0.f;
+
+            // operands the epilogue needs from global memory are requested *before* waiting for the
+            // accumulator, so their latency hides under the MMAs of this tile
+            uint4 pre[(MODE == kDx) ? CHUNKS * 4 : 1];
+            if (MODE == kDx && row_ok) {
+                const uint4* cp = reinterpret_cast<const uint4*>(g.cprev + (size_t)b * g.cprev_fit + (size_t)row * g.N + col_base);
+#pragma unroll
+                for (int j = 0; j < CHUNKS * 4; ++j) pre[j] = __ldg(cp + j);
+            }
+            float omega = 0.f;
+            if (MODE == kFwdSine || MODE == kDx || MODE == kFwdDot) omega = rec->omega;
+
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+            const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
+#pragma unroll
             for (int c = 0; c < CHUNKS; ++c) {
-                const int col_in_tile = half * (BN / 2) + c * 32;
-                const int col = nt * BN + col_in_tile;
+                const int col = col_base + c * 32;
                 uint32_t v[32];
-                tmem_ld32(t_row + col_in_tile, v);
+                tmem_ld32(t_row + c * 32, v);
                 tmem_ld_wait();
                 if (MODE == kRaw || MODE == kDw) {
                     if (row_ok) {
@@ -303,22 +315,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
-                } else if (MODE == kFwdSine) {
+                } else if (MODE == kFwdSine || MODE == kFwdDot) {
                     const float* bias = rec->params + g.bias_off + col;
-                    const float omega = rec->omega;
                     uint32_t so[16], co[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
-                        float s0, c0, s1, c1, s2, c2, s3, c3;
-                        sincosf(omega * (__uint_as_float(v[j + 0]) + bb.x), &s0, &c0);
-                        sincosf(omega * (__uint_as_float(v[j + 1]) + bb.y), &s1, &c1);
-                        sincosf(omega * (__uint_as_float(v[j + 2]) + bb.z), &s2, &c2);
-                        sincosf(omega * (__uint_as_float(v[j + 3]) + bb.w), &s3, &c3);
-                        so[j / 2] = pack_bf16(s0, s1); so[j / 2 + 1] = pack_bf16(s2, s3);
-                        co[j / 2] = pack_bf16(c0, c1); co[j / 2 + 1] = pack_bf16(c2, c3);
+                    for (int h16 = 0; h16 < 2; ++h16) {          // 16 independent sincos chains at a time
+                        float arg[16], sn[16], cs[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + h16 * 16 + j));
+                            arg[j + 0] = omega * (__uint_as_float(v[h16 * 16 + j + 0]) + bb.x);
+                            arg[j + 1] = omega * (__uint_as_float(v[h16 * 16 + j + 1]) + bb.y);
+                            arg[j + 2] = omega * (__uint_as_float(v[h16 * 16 + j + 2]) + bb.z);
+                            arg[j + 3] = omega * (__uint_as_float(v[h16 * 16 + j + 3]) + bb.w);
+                        }
+                        sincos_group(arg, sn, cs);
+                        if (MODE == kFwdDot) {
+                            const float* u = g.dotvec + (size_t)b * g.dotvec_fit + col + h16 * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 uu = __ldg(reinterpret_cast<const float4*>(u + j));
+                                sq = fmaf(uu.x, sn[j], sq); sq = fmaf(uu.y, sn[j + 1], sq);
+                                sq = fmaf(uu.z, sn[j + 2], sq); sq = fmaf(uu.w, sn[j + 3], sq);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                so[h16 * 8 + j / 2] = pack_bf16(sn[j], sn[j + 1]);
+                                co[h16 * 8 + j / 2] = pack_bf16(cs[j], cs[j + 1]);
+                            }
+                        }
                     }
-                    if (row_ok) {
+                    if (MODE == kFwdSine && row_ok) {
                         const size_t o = (size_t)row * g.N + col;
                         uint4* d0 = reinterpret_cast<uint4*>(g.out0 + (size_t)b * g.out0_fit + o);
 #pragma unroll
@@ -329,32 +357,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             for (int j = 0; j < 4; ++j) d1[j] = make_uint4(co[4 * j], co[4 * j + 1], co[4 * j + 2], co[4 * j + 3]);
                         }
                     }
-                } else if (MODE == kFwdDot) {
-                    const float* bias = rec->params + g.bias_off + col;
-                    const float* u = g.dotvec + (size_t)b * g.dotvec_fit + col;
-                    const float omega = rec->omega;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
-                        const float4 uu = __ldg(reinterpret_cast<const float4*>(u + j));
-                        sq = fmaf(uu.x, sinf(omega * (__uint_as_float(v[j + 0]) + bb.x)), sq);
-                        sq = fmaf(uu.y, sinf(omega * (__uint_as_float(v[j + 1]) + bb.y)), sq);
-                        sq = fmaf(uu.z, sinf(omega * (__uint_as_float(v[j + 2]) + bb.z)), sq);
-                        sq = fmaf(uu.w, sinf(omega * (__uint_as_float(v[j + 3]) + bb.w)), sq);
-                    }
                 } else if (MODE == kFwdOut) {
                     const float* bias = rec->params + g.bias_off + col;
                     uint32_t dout[16];
                     if (row_ok) {
                         const float* tn = rec->tnorm + (size_t)row * g.N + col;
+                        float4 tt[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) tt[j] = __ldg(reinterpret_cast<const float4*>(tn) + j);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
-                            const float4 tt = __ldg(reinterpret_cast<const float4*>(tn + j));
-                            const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - tt.x;
-                            const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - tt.y;
-                            const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - tt.z;
-                            const float e3 = (__uint_as_float(v[j + 3]) + bb.w) - tt.w;
+                            const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - tt[j / 4].x;
+                            const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - tt[j / 4].y;
+                            const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - tt[j / 4].z;
+                            const float e3 = (__uint_as_float(v[j + 3]) + bb.w) - tt[j / 4].w;
                             sq = fmaf(e0, e0, sq); sq = fmaf(e1, e1, sq); sq = fmaf(e2, e2, sq); sq = fmaf(e3, e3, sq);
                             dout[j / 2] = pack_bf16(e0 * g.loss_scale, e1 * g.loss_scale);
                             dout[j / 2 + 1] = pack_bf16(e2 * g.loss_scale, e3 * g.loss_scale);
@@ -365,13 +382,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 } else if (MODE == kDx) {
                     if (row_ok) {
-                        const size_t o = (size_t)row * g.N + col;
-                        const uint4* cp = reinterpret_cast<const uint4*>(g.cprev + (size_t)b * g.cprev_fit + o);
-                        const float omega = rec->omega;
                         uint32_t dout[16];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 cc = __ldg(cp + j);
+                            const uint4 cc = pre[c * 4 + j];
                             const uint32_t cu[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -382,14 +396,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                 dout[j * 4 + t] = pack_bf16(d0v, d1v);
                             }
                         }
-                        uint4* d0 = reinterpret_cast<uint4*>(g.out0 + (size_t)b * g.out0_fit + o);
+                        uint4* d0 = reinterpret_cast<uint4*>(g.out0 + (size_t)b * g.out0_fit + (size_t)row * g.N + col);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) d0[j] = make_uint4(dout[4 * j], dout[4 * j + 1], dout[4 * j + 2], dout[4 * j + 3]);
                     }
                 }
             }
             if (MODE == kDw && half == 0 && nt == 0) {
-                const uint32_t dbv = tmem_ld1(t_row + BN);      // every column of the ones-product equals db[row]
+                const uint32_t dbv = tmem_ld1(tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + BN);   // every column of the ones-product equals db[row]
                 tmem_ld_wait();
                 if (row_ok) g.biasgrad[(size_t)b * g.biasgrad_fit + row] = __uint_as_float(dbv);
             }
@@ -569,8 +583,8 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
     const size_t nh = (size_t)N * H, nd = (size_t)N * D;
     int rc;
     {
-        const size_t total4 = nh / 4;
-        dim3 grid((unsigned)ceil_div(total4, (size_t)256), nf);
+        const size_t total8 = nh / 8;
+        dim3 grid((unsigned)ceil_div(total8, (size_t)256), nf);
         f32::layer0_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(recs, N, H, (__nv_bfloat16*)act[0], (__nv_bfloat16*)cosb[0], nh);
     }
     TcArgs base{};
