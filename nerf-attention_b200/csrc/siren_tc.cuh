@@ -156,6 +156,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100): one full 32 B sector per lane, so the
+// row-per-thread epilogue never issues partial-sector writes and needs half the LSU instructions
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t* v) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -278,52 +289,54 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;             // which half of the BN columns
         constexpr int CHUNKS = BN / 64;               // 32-column chunks per warp
+        constexpr bool kHeavy = (MODE == kFwdSine || MODE == kFwdDot);   // big inlined bodies: keep the chunk loop rolled
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int nt = tile % g.n_tiles, mt = (tile / g.n_tiles) % g.m_tiles, b = tile / (g.n_tiles * g.m_tiles);
             const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
-            const FitRec* rec = g.recs ? &g.recs[b] : nullptr;
             const int row = mt * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
             const int col_base = nt * BN + half * (BN / 2);
             float sq = 0.f;
 
-            // operands the epilogue needs from global memory are requested *before* waiting for the
-            // accumulator, so their latency hides under the MMAs of this tile
-            uint4 pre[(MODE == kDx) ? CHUNKS * 4 : 1];
-            if (MODE == kDx && row_ok) {
-                const uint4* cp = reinterpret_cast<const uint4*>(g.cprev + (size_t)b * g.cprev_fit + (size_t)row * g.N + col_base);
-#pragma unroll
-                for (int j = 0; j < CHUNKS * 4; ++j) pre[j] = __ldg(cp + j);
-            }
+            // everything the epilogue needs from global memory is requested *before* waiting for the
+            // accumulator, so the latency hides under the MMAs of this tile
             float omega = 0.f;
-            if (MODE == kFwdSine || MODE == kDx || MODE == kFwdDot) omega = rec->omega;
+            const float* bias = nullptr;
+            const float* tn = nullptr;
+            if (MODE == kFwdSine || MODE == kDx || MODE == kFwdDot || MODE == kFwdOut) {
+                const FitRec* rec = &g.recs[b];
+                omega = rec->omega;
+                if (MODE != kDx) bias = rec->params + g.bias_off + col_base;
+                if (MODE == kFwdOut) tn = rec->tnorm + (size_t)row * g.N + col_base;
+            }
+            uint32_t pre[(MODE == kDx) ? CHUNKS * 16 : 1];
+            if (MODE == kDx && row_ok) {
+                const __nv_bfloat16* cp = g.cprev + (size_t)b * g.cprev_fit + (size_t)row * g.N + col_base;
+#pragma unroll
+                for (int j = 0; j < CHUNKS * 2; ++j) ld_global_nc_256(cp + j * 16, &pre[j * 8]);
+            }
 
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
-#pragma unroll
-            for (int c = 0; c < CHUNKS; ++c) {
+
+            auto process = [&](const uint32_t (&v)[32], int c) {
                 const int col = col_base + c * 32;
-                uint32_t v[32];
-                tmem_ld32(t_row + c * 32, v);
-                tmem_ld_wait();
                 if (MODE == kRaw || MODE == kDw) {
                     if (row_ok) {
                         float* dst = g.fout + (size_t)b * g.fout_fit + g.fout_off + (size_t)row * g.ldf + col;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; j += 8) st_global_256(dst + j, &v[j]);
                     }
                 } else if (MODE == kFwdSine || MODE == kFwdDot) {
-                    const float* bias = rec->params + g.bias_off + col;
                     uint32_t so[16], co[16];
 #pragma unroll
                     for (int h16 = 0; h16 < 2; ++h16) {          // 16 independent sincos chains at a time
                         float arg[16], sn[16], cs[16];
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + h16 * 16 + j));
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + h16 * 16 + j));
                             arg[j + 0] = omega * (__uint_as_float(v[h16 * 16 + j + 0]) + bb.x);
                             arg[j + 1] = omega * (__uint_as_float(v[h16 * 16 + j + 1]) + bb.y);
                             arg[j + 2] = omega * (__uint_as_float(v[h16 * 16 + j + 2]) + bb.z);
@@ -348,58 +361,73 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                     if (MODE == kFwdSine && row_ok) {
                         const size_t o = (size_t)row * g.N + col;
-                        uint4* d0 = reinterpret_cast<uint4*>(g.out0 + (size_t)b * g.out0_fit + o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) d0[j] = make_uint4(so[4 * j], so[4 * j + 1], so[4 * j + 2], so[4 * j + 3]);
+                        __nv_bfloat16* d0 = g.out0 + (size_t)b * g.out0_fit + o;
+                        st_global_256(d0, &so[0]); st_global_256(d0 + 16, &so[8]);
                         if (g.out1) {
-                            uint4* d1 = reinterpret_cast<uint4*>(g.out1 + (size_t)b * g.out1_fit + o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) d1[j] = make_uint4(co[4 * j], co[4 * j + 1], co[4 * j + 2], co[4 * j + 3]);
+                            __nv_bfloat16* d1 = g.out1 + (size_t)b * g.out1_fit + o;
+                            st_global_256(d1, &co[0]); st_global_256(d1 + 16, &co[8]);
                         }
                     }
                 } else if (MODE == kFwdOut) {
-                    const float* bias = rec->params + g.bias_off + col;
-                    uint32_t dout[16];
                     if (row_ok) {
-                        const float* tn = rec->tnorm + (size_t)row * g.N + col;
-                        float4 tt[8];
+                        uint32_t tt[32], dout[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) tt[j] = __ldg(reinterpret_cast<const float4*>(tn) + j);
+                        for (int j = 0; j < 32; j += 8) ld_global_nc_256(tn + c * 32 + j, &tt[j]);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
-                            const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - tt[j / 4].x;
-                            const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - tt[j / 4].y;
-                            const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - tt[j / 4].z;
-                            const float e3 = (__uint_as_float(v[j + 3]) + bb.w) - tt[j / 4].w;
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + j));
+                            const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - __uint_as_float(tt[j + 0]);
+                            const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - __uint_as_float(tt[j + 1]);
+                            const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - __uint_as_float(tt[j + 2]);
+                            const float e3 = (__uint_as_float(v[j + 3]) + bb.w) - __uint_as_float(tt[j + 3]);
                             sq = fmaf(e0, e0, sq); sq = fmaf(e1, e1, sq); sq = fmaf(e2, e2, sq); sq = fmaf(e3, e3, sq);
                             dout[j / 2] = pack_bf16(e0 * g.loss_scale, e1 * g.loss_scale);
                             dout[j / 2 + 1] = pack_bf16(e2 * g.loss_scale, e3 * g.loss_scale);
                         }
-                        uint4* d0 = reinterpret_cast<uint4*>(g.out0 + (size_t)b * g.out0_fit + (size_t)row * g.N + col);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) d0[j] = make_uint4(dout[4 * j], dout[4 * j + 1], dout[4 * j + 2], dout[4 * j + 3]);
+                        __nv_bfloat16* d0 = g.out0 + (size_t)b * g.out0_fit + (size_t)row * g.N + col;
+                        st_global_256(d0, &dout[0]); st_global_256(d0 + 16, &dout[8]);
                     }
                 } else if (MODE == kDx) {
                     if (row_ok) {
                         uint32_t dout[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 cc = pre[c * 4 + j];
-                            const uint32_t cu[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                float c0, c1;
-                                unpack_bf16(cu[t], c0, c1);
-                                const float d0v = __uint_as_float(v[j * 8 + t * 2]) * (omega * c0);
-                                const float d1v = __uint_as_float(v[j * 8 + t * 2 + 1]) * (omega * c1);
-                                dout[j * 4 + t] = pack_bf16(d0v, d1v);
-                            }
+                        for (int t = 0; t < 16; ++t) {
+                            float c0, c1;
+                            unpack_bf16(pre[c * 16 + t], c0, c1);
+                            dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * c0),
+                                                __uint_as_float(v[2 * t + 1]) * (omega * c1));
                         }
-                        uint4* d0 = reinterpret_cast<uint4*>(g.out0 + (size_t)b * g.out0_fit + (size_t)row * g.N + col);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) d0[j] = make_uint4(dout[4 * j], dout[4 * j + 1], dout[4 * j + 2], dout[4 * j + 3]);
+                        __nv_bfloat16* d0 = g.out0 + (size_t)b * g.out0_fit + (size_t)row * g.N + col;
+                        st_global_256(d0, &dout[0]); st_global_256(d0 + 16, &dout[8]);
                     }
+                }
+            };
+
+            // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row, va);
+            if constexpr (CHUNKS == 1) {
+                tmem_ld_wait();
+                process(va, 0);
+            } else if constexpr (kHeavy) {
+#pragma unroll 1
+                for (int c = 0; c < CHUNKS; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32(t_row + (c + 1) * 32, vb);
+                    process(va, c);
+                    tmem_ld_wait();
+                    if (c + 2 < CHUNKS) tmem_ld32(t_row + (c + 2) * 32, va);
+                    process(vb, c + 1);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CHUNKS; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32(t_row + (c + 1) * 32, vb);
+                    process(va, c);
+                    tmem_ld_wait();
+                    if (c + 2 < CHUNKS) tmem_ld32(t_row + (c + 2) * 32, va);
+                    process(vb, c + 1);
                 }
             }
             if (MODE == kDw && half == 0 && nt == 0) {
