@@ -146,6 +146,8 @@ def cpu_sample(seq_len: int, epochs: int, warm: int = 3) -> dict:
     from nerf_attention.extract import synthetic_head
     from nerf_attention.types import CONFIGS_FULL
     from oracle import siren_oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1; the CPU leg is meant to use the box's host cores
+    torch.set_num_threads(max(1, int(os.environ.get('NERFATTN_CPU_THREADS', os.cpu_count() or 1))))
     kv, _ = synthetic_head(16, 0, seq_len, NUM_LAYERS, NUM_KV_HEADS, HEAD_DIM)
     per_cfg, total = {}, 0.0
     for ci, cfg in enumerate(CONFIGS_FULL):

@@ -317,6 +317,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int j = 0; j < CHUNKS * 2; ++j) ld_global_nc_256(cp + j * 16, &pre[j * 8]);
             }
 
+            float bcur[kHeavy ? 16 : 1];
+            if (kHeavy) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
+                    bcur[j] = bb.x; bcur[j + 1] = bb.y; bcur[j + 2] = bb.z; bcur[j + 3] = bb.w;
+                }
+            }
+
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
@@ -335,12 +344,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int h16 = 0; h16 < 2; ++h16) {          // 16 independent sincos chains at a time
                         float arg[16], sn[16], cs[16];
 #pragma unroll
+                        for (int j = 0; j < 16; ++j) arg[j] = omega * (__uint_as_float(v[h16 * 16 + j]) + bcur[j]);
+                        // bias of the *next* group is requested now: ~450 instructions of distance hide the L1 latency
+                        const int next = (c * 2 + h16 + 1 < CHUNKS * 2) ? (c * 2 + h16 + 1) * 16 : 0;
+#pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + h16 * 16 + j));
-                            arg[j + 0] = omega * (__uint_as_float(v[h16 * 16 + j + 0]) + bb.x);
-                            arg[j + 1] = omega * (__uint_as_float(v[h16 * 16 + j + 1]) + bb.y);
-                            arg[j + 2] = omega * (__uint_as_float(v[h16 * 16 + j + 2]) + bb.z);
-                            arg[j + 3] = omega * (__uint_as_float(v[h16 * 16 + j + 3]) + bb.w);
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + next + j));
+                            bcur[j] = bb.x; bcur[j + 1] = bb.y; bcur[j + 2] = bb.z; bcur[j + 3] = bb.w;
                         }
                         sincos_group(arg, sn, cs);
                         if (MODE == kFwdDot) {
