@@ -16,34 +16,49 @@ namespace dec {
 
 // ---------------------------------------------------------------------------
 // Baseline: scores[i][t] = q[i] . K[i][t],  K fp16 [n][N][D] streamed once from HBM.
-// G = D/8 lanes share a row (16 B per lane, one 128-bit load each), UNROLL rows in flight
-// per lane group; grid-stride over rows with a grid sized to a multiple of the SM count.
+// G = D/16 lanes share a row: one 256-bit load (a full 32 B sector) per lane per row, UNROLL
+// rows in flight per lane group, streaming (no-allocate) loads; grid-stride over row groups
+// with a grid that is a multiple of the SM count.
 template <int G>
 __global__ void __launch_bounds__(256)
-kvread_qk_kernel(const uint4* __restrict__ K, const uint4* __restrict__ q, float* __restrict__ scores,
+kvread_qk_kernel(const uint32_t* __restrict__ K, const uint32_t* __restrict__ q, float* __restrict__ scores,
                  long long rows_total, int N) {
-    constexpr int UNROLL = 4;
+    constexpr int UNROLL = 8;
     const int lane_in_group = threadIdx.x % G;
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const long long ngroups = (long long)gridDim.x * blockDim.x / G;
     for (long long r0 = group * UNROLL; r0 < rows_total; r0 += ngroups * UNROLL) {
-        uint4 kv[UNROLL];
+        uint32_t kv[UNROLL][8];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u;
-            kv[u] = (r < rows_total) ? __ldcs(K + r * G + lane_in_group) : make_uint4(0, 0, 0, 0);
+            if (r < rows_total) {
+                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(kv[u][0]), "=r"(kv[u][1]), "=r"(kv[u][2]), "=r"(kv[u][3]), "=r"(kv[u][4]),
+                               "=r"(kv[u][5]), "=r"(kv[u][6]), "=r"(kv[u][7])
+                             : "l"(K + (r * G + lane_in_group) * 8));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) kv[u][j] = 0u;
+            }
         }
+        long long head_cached = -1;
+        uint32_t qv[8];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long r = r0 + u;
             const long long head = (r < rows_total) ? r / N : 0;
-            const uint4 qv = __ldg(q + head * G + lane_in_group);
-            const __half2* kh = reinterpret_cast<const __half2*>(&kv[u]);
-            const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+            if (head != head_cached) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(q + (head * G + lane_in_group) * 8));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(q + (head * G + lane_in_group) * 8 + 4));
+                qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
+                head_cached = head;
+            }
             float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 kf = __half22float2(kh[j]), qf = __half22float2(qh[j]);
+            for (int j = 0; j < 8; ++j) {
+                const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&kv[u][j]));
+                const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qv[j]));
                 acc = fmaf(kf.x, qf.x, acc);
                 acc = fmaf(kf.y, qf.y, acc);
             }

@@ -736,16 +736,16 @@ extern "C" int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float*
     if (!k_fp16 || !q_fp16 || !scores || n <= 0 || N <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
     if (D != 64 && D != 128 && D != 256) { set_error("kvread: D must be 64, 128 or 256"); return NA_ERR_UNSUPPORTED; }
     const long long rows = (long long)n * N;
-    const int G = D / 8;
-    const long long groups_needed = (rows + 3) / 4;
+    const int G = D / 16;                                        // lanes per row, 32 B each
+    const long long groups_needed = (rows + 7) / 8;
     long long blocks = (groups_needed * G + 255) / 256;
     const long long cap = (long long)tc::num_sms() * 8;         // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const uint4* K = (const uint4*)k_fp16; const uint4* q = (const uint4*)q_fp16;
-    if (G == 8) dec::kvread_qk_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
-    else if (G == 16) dec::kvread_qk_kernel<16><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
-    else dec::kvread_qk_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
+    const uint32_t* K = (const uint32_t*)k_fp16; const uint32_t* q = (const uint32_t*)q_fp16;
+    if (G == 4) dec::kvread_qk_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
+    else if (G == 8) dec::kvread_qk_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
+    else dec::kvread_qk_kernel<16><<<(unsigned)blocks, 256, 0, stream>>>(K, q, scores, rows, N);
     NA_LAUNCH_OK("kvread_qk_kernel");
     return NA_OK;
 }

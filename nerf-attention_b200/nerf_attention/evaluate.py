@@ -76,6 +76,7 @@ class PackedModels:
         self.device = dev
         self._ws = {}
         self._decode_out = {}
+        self._decode_ptrs = {}
 
     def _workspace(self, kind: str, size_fn, *args) -> torch.Tensor:
         if kind not in self._ws:
@@ -90,7 +91,8 @@ class PackedModels:
         if out is None:
             out = torch.empty(self.n, self.seq_len, self.d, device=self.device)
         ws = self._workspace('nerfattn_forward_workspace_bytes', lib.nerfattn_forward_workspace_bytes)
-        ptrs = (ctypes.c_void_p * self.n)(*[out[i].data_ptr() for i in range(self.n)])
+        base, stride = out.data_ptr(), out.stride(0) * 4
+        ptrs = (ctypes.c_void_p * self.n)(*[base + i * stride for i in range(self.n)])
         _native.check(lib.nerfattn_siren_forward(self.fits, self.n, int(denormalise), ptrs, ws.data_ptr(),
                                                  ws.numel(), _native.stream_handle()), 'nerfattn_siren_forward')
         return out
@@ -108,9 +110,12 @@ class PackedModels:
             out = cached
         elif out is None:
             out = torch.empty(self.n, self.seq_len, device=self.device)
-        self._decode_out[prec] = out
         ws = self._workspace(f'nerfattn_decode_workspace_bytes/{prec}', lib.nerfattn_decode_workspace_bytes, prec)
-        ptrs = (ctypes.c_void_p * self.n)(*[out[i].data_ptr() for i in range(self.n)])
+        if not reuse_setup or prec not in self._decode_ptrs:
+            base, stride = out.data_ptr(), out.stride(0) * 4
+            self._decode_ptrs[prec] = (ctypes.c_void_p * self.n)(*[base + i * stride for i in range(self.n)])
+        self._decode_out[prec] = out
+        ptrs = self._decode_ptrs[prec]
         assert q.dtype == torch.float16 and q.is_contiguous() and q.shape == (self.n, self.d)
         _native.check(lib.nerfattn_decode_qk(self.fits, self.n, q.data_ptr(), ptrs, prec, int(reuse_setup),
                                              ws.data_ptr(), ws.numel(), _native.stream_handle()),
