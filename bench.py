@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument('--epochs', type=int, default=2000)
     ap.add_argument('--seq_len', type=int, default=2048)
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end and CPU legs (profiling runs)')
-    ap.add_argument('--cpu-epochs', type=int, default=40, help='epochs per architecture in the CPU sample')
+    ap.add_argument('--cpu-epochs', type=int, default=300, help='epochs per architecture in the CPU sample')
     return ap.parse_args()
 
 

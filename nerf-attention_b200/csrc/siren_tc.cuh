@@ -15,6 +15,8 @@
 
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -30,16 +32,21 @@ constexpr int NTHREADS = 64 + NUM_EPI_WARPS * 32;   // 320
 constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16 KB
 constexpr int ONES_BYTES = 16 * BK * 2;             // 2 KB, B operand of the bias-gradient MMA
 
+constexpr int kDefaultOcc2Mask = 0;     // tuned on B200, see profiles/README.md
 enum Mode { kRaw = 0, kFwdSine = 1, kFwdOut = 2, kDx = 3, kDw = 4, kFwdDot = 5 };
 
-template <int BN> struct Cfg {
+// OCC = CTAs per SM the kernel is sized for.  OCC 1: deep smem ring, double-buffered accumulator,
+// 16-wide sincos groups.  OCC 2: <= 113 KB smem and <= 256 TMEM columns per CTA so that two CTAs
+// (possibly of two different kernels: a sincos-bound forward and an HBM-bound backward of another
+// group) share an SM and fill each other's stalls.
+template <int BN, int OCC> struct Cfg {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (OCC == 1) ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 2 : (BN == 128) ? 3 : 4);
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 };
 // barriers (2*STAGES + 4) * 8 B + tmem slot, rounded up; + 1 KB slack for the 1024 B alignment
-template <int BN> constexpr int smem_bytes() {
-    return Cfg<BN>::STAGES * Cfg<BN>::STAGE_BYTES + ONES_BYTES + 256 + 1024;
+template <int BN, int OCC> constexpr int smem_bytes() {
+    return Cfg<BN, OCC>::STAGES * Cfg<BN, OCC>::STAGE_BYTES + ONES_BYTES + 256 + 1024;
 }
 
 struct TcArgs {
@@ -177,15 +184,18 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& a, float& b) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, bool A_MN, bool B_MN, int BN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int MODE, bool A_MN, bool B_MN, int BN, int OCC>
+__global__ void __launch_bounds__(NTHREADS, OCC)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcArgs g) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, OCC>;
     constexpr int STAGES = C::STAGES;
     constexpr int ACC_STRIDE = (MODE == kDw) ? BN + 32 : BN;       // TMEM columns per accumulator stage
-    constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 32) ? 32 : (2 * ACC_STRIDE <= 64) ? 64 :
-                              (2 * ACC_STRIDE <= 128) ? 128 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
-    static_assert(2 * ACC_STRIDE <= 512, "accumulators do not fit TMEM");
+    constexpr int TMEM_BUDGET = 512 / OCC;
+    constexpr int NACC = (2 * ACC_STRIDE <= TMEM_BUDGET) ? 2 : 1;  // accumulator stages
+    constexpr int TMEM_NEED = NACC * ACC_STRIDE;
+    constexpr int TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 :
+                              (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
+    static_assert(TMEM_COLS <= TMEM_BUDGET, "accumulators do not fit the TMEM share of this CTA");
     static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
 
     extern __shared__ uint8_t smem_raw[];
@@ -259,7 +269,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         constexpr uint32_t B_KADV = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         int stage = 0; uint32_t phase = 0; int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            const int as = iter % NACC; const uint32_t aphase = (iter / NACC) & 1;
             mbar_wait(&tmem_empty[as], aphase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
@@ -293,7 +303,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int nt = tile % g.n_tiles, mt = (tile / g.n_tiles) % g.m_tiles, b = tile / (g.n_tiles * g.m_tiles);
-            const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            const int as = iter % NACC; const uint32_t aphase = (iter / NACC) & 1;
             const int row = mt * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
             const int col_base = nt * BN + half * (BN / 2);
@@ -317,10 +327,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int j = 0; j < CHUNKS * 2; ++j) ld_global_nc_256(cp + j * 16, &pre[j * 8]);
             }
 
-            float bcur[kHeavy ? 16 : 1];
+            constexpr int BW = kHeavy ? ((OCC == 1) ? 16 : 8) : 1;
+            float bcur[BW];
             if (kHeavy) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
+                for (int j = 0; j < BW; j += 4) {
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + j));
                     bcur[j] = bb.x; bcur[j + 1] = bb.y; bcur[j + 2] = bb.z; bcur[j + 3] = bb.w;
                 }
@@ -340,32 +351,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 } else if (MODE == kFwdSine || MODE == kFwdDot) {
                     uint32_t so[16], co[16];
+                    constexpr int GW = (OCC == 1) ? 16 : 8;      // independent sincos chains per group
 #pragma unroll
-                    for (int h16 = 0; h16 < 2; ++h16) {          // 16 independent sincos chains at a time
-                        float arg[16], sn[16], cs[16];
+                    for (int gi = 0; gi < 32 / GW; ++gi) {
+                        float arg[GW], sn[GW], cs[GW];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) arg[j] = omega * (__uint_as_float(v[h16 * 16 + j]) + bcur[j]);
-                        // bias of the *next* group is requested now: ~450 instructions of distance hide the L1 latency
-                        const int next = (c * 2 + h16 + 1 < CHUNKS * 2) ? (c * 2 + h16 + 1) * 16 : 0;
+                        for (int j = 0; j < GW; ++j) arg[j] = omega * (__uint_as_float(v[gi * GW + j]) + bcur[j]);
+                        // bias of the *next* group is requested now: a whole group of math hides the L1 latency
+                        const int gidx = c * (32 / GW) + gi + 1;
+                        const int next = (gidx < CHUNKS * (32 / GW)) ? gidx * GW : 0;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
+                        for (int j = 0; j < GW; j += 4) {
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + next + j));
                             bcur[j] = bb.x; bcur[j + 1] = bb.y; bcur[j + 2] = bb.z; bcur[j + 3] = bb.w;
                         }
                         sincos_group(arg, sn, cs);
                         if (MODE == kFwdDot) {
-                            const float* u = g.dotvec + (size_t)b * g.dotvec_fit + col + h16 * 16;
+                            const float* u = g.dotvec + (size_t)b * g.dotvec_fit + col + gi * GW;
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
+                            for (int j = 0; j < GW; j += 4) {
                                 const float4 uu = __ldg(reinterpret_cast<const float4*>(u + j));
                                 sq = fmaf(uu.x, sn[j], sq); sq = fmaf(uu.y, sn[j + 1], sq);
                                 sq = fmaf(uu.z, sn[j + 2], sq); sq = fmaf(uu.w, sn[j + 3], sq);
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                so[h16 * 8 + j / 2] = pack_bf16(sn[j], sn[j + 1]);
-                                co[h16 * 8 + j / 2] = pack_bf16(cs[j], cs[j + 1]);
+                            for (int j = 0; j < GW; j += 2) {
+                                so[(gi * GW + j) / 2] = pack_bf16(sn[j], sn[j + 1]);
+                                co[(gi * GW + j) / 2] = pack_bf16(cs[j], cs[j + 1]);
                             }
                         }
                     }
@@ -413,31 +426,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             };
 
-            // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
-            uint32_t va[32], vb[32];
-            tmem_ld32(t_row, va);
-            if constexpr (CHUNKS == 1) {
-                tmem_ld_wait();
-                process(va, 0);
-            } else if constexpr (kHeavy) {
+            if constexpr (OCC == 1 && CHUNKS > 1) {
+                // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+                uint32_t va[32], vb[32];
+                tmem_ld32(t_row, va);
+                if constexpr (kHeavy) {
 #pragma unroll 1
-                for (int c = 0; c < CHUNKS; c += 2) {
-                    tmem_ld_wait();
-                    tmem_ld32(t_row + (c + 1) * 32, vb);
-                    process(va, c);
-                    tmem_ld_wait();
-                    if (c + 2 < CHUNKS) tmem_ld32(t_row + (c + 2) * 32, va);
-                    process(vb, c + 1);
+                    for (int c = 0; c < CHUNKS; c += 2) {
+                        tmem_ld_wait();
+                        tmem_ld32(t_row + (c + 1) * 32, vb);
+                        process(va, c);
+                        tmem_ld_wait();
+                        if (c + 2 < CHUNKS) tmem_ld32(t_row + (c + 2) * 32, va);
+                        process(vb, c + 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; c += 2) {
+                        tmem_ld_wait();
+                        tmem_ld32(t_row + (c + 1) * 32, vb);
+                        process(va, c);
+                        tmem_ld_wait();
+                        if (c + 2 < CHUNKS) tmem_ld32(t_row + (c + 2) * 32, va);
+                        process(vb, c + 1);
+                    }
                 }
             } else {
+                // two CTAs per SM: the co-resident CTA hides the TMEM latency, keep registers low
+                uint32_t va[32];
+                if constexpr (kHeavy) {
+#pragma unroll 1
+                    for (int c = 0; c < CHUNKS; ++c) { tmem_ld32(t_row + c * 32, va); tmem_ld_wait(); process(va, c); }
+                } else {
 #pragma unroll
-                for (int c = 0; c < CHUNKS; c += 2) {
-                    tmem_ld_wait();
-                    tmem_ld32(t_row + (c + 1) * 32, vb);
-                    process(va, c);
-                    tmem_ld_wait();
-                    if (c + 2 < CHUNKS) tmem_ld32(t_row + (c + 2) * 32, va);
-                    process(vb, c + 1);
+                    for (int c = 0; c < CHUNKS; ++c) { tmem_ld32(t_row + c * 32, va); tmem_ld_wait(); process(va, c); }
                 }
             }
             if (MODE == kDw && half == 0 && nt == 0) {
@@ -587,17 +609,32 @@ inline int num_sms() {
     return n;
 }
 
-template <int MODE, bool A_MN, bool B_MN, int BN>
-inline int launch_one(const GemmMaps& maps, TcArgs a, cudaStream_t s) {
-    constexpr int smem = smem_bytes<BN>();
+// bit m of the mask selects the 2-CTA/SM variant for Mode m (NERFATTN_OCC2 overrides the default)
+inline unsigned occ2_mask() {
+    static int mask = -1;
+    if (mask < 0) {
+        const char* e = getenv("NERFATTN_OCC2");
+        mask = e ? (int)strtol(e, nullptr, 0) : kDefaultOcc2Mask;
+    }
+    return (unsigned)mask;
+}
+
+template <int MODE, bool A_MN, bool B_MN, int BN, int OCC>
+inline int launch_occ(const GemmMaps& maps, TcArgs a, cudaStream_t s) {
+    constexpr int smem = smem_bytes<BN, OCC>();
     a.m_tiles = ceil_div(a.M, BM);
     a.n_tiles = a.N / BN;
     const int tiles = a.nb * a.m_tiles * a.n_tiles;
-    const int grid = std::min(tiles, num_sms());
-    tc_gemm_kernel<MODE, A_MN, B_MN, BN><<<grid, NTHREADS, smem, s>>>(maps.a, maps.b, a);
+    const int grid = std::min(tiles, num_sms() * OCC);
+    tc_gemm_kernel<MODE, A_MN, B_MN, BN, OCC><<<grid, NTHREADS, smem, s>>>(maps.a, maps.b, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("tc_gemm launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
+}
+template <int MODE, bool A_MN, bool B_MN, int BN>
+inline int launch_one(const GemmMaps& maps, const TcArgs& a, cudaStream_t s) {
+    if ((occ2_mask() >> MODE) & 1u) return launch_occ<MODE, A_MN, B_MN, BN, 2>(maps, a, s);
+    return launch_occ<MODE, A_MN, B_MN, BN, 1>(maps, a, s);
 }
 
 template <int MODE, bool A_MN, bool B_MN>
@@ -666,8 +703,11 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
 // cudaFuncSetAttribute for every instantiation, once, outside any stream capture.
 template <int MODE, bool A_MN, bool B_MN, int BN>
 inline cudaError_t configure_one() {
-    return cudaFuncSetAttribute(tc_gemm_kernel<MODE, A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                smem_bytes<BN>());
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE, A_MN, B_MN, BN, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, 1>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_gemm_kernel<MODE, A_MN, B_MN, BN, 2>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, 2>());
 }
 inline int configure_all() {
     static std::once_flag once;
