@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NERFATTN_ABI_VERSION 4
+#define NERFATTN_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define NA_API __attribute__((visibility("default")))
@@ -177,6 +177,15 @@ NA_API int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float* sco
 NA_API int nerfattn_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, float* c,
                              int32_t M, int32_t N, int32_t K, int32_t batch,
                              int32_t a_mn_major, int32_t b_mn_major, na_stream_t stream);
+
+/*
+ * Diagnostic: s[i], c[i] = sin, cos of x[i] (device fp32 arrays of n values) through the
+ * device functions the epilogues use.  mode 0: branch-free polynomial (fp32 path, layer 0),
+ * mode 1: exact Cody-Waite reduction + SFU core (hidden layers of the BF16 path, whose results
+ * are rounded to bf16).  Replaces torch.sin (siren.py:34); the tests bound both against float64.
+ */
+NA_API int nerfattn_debug_sincos(const float* x, float* s, float* c, int64_t n, int32_t mode,
+                          na_stream_t stream);
 
 #ifdef __cplusplus
 }

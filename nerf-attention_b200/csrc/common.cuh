@@ -141,6 +141,32 @@ __device__ __forceinline__ void sincos_group(const float (&x)[N], float (&s)[N],
     }
 }
 
+// Tensor-path variant for values that are rounded to bf16 right away: the same exact-in-fp32
+// Cody-Waite reduction (here by 2*pi, so no quadrant fix-up is needed), then the SFU evaluates
+// sin/cos of the reduced argument in [-pi, pi], where MUFU.SIN/COS have their documented
+// 2^-21.4 absolute error.  Total |error| <= 5e-7 (tests/test_gpu_tc.py::test_sincos_accuracy),
+// four orders of magnitude below the bf16 rounding (2^-9 relative) applied to the result; what
+// rules out bare __sinf at omega_0 = 60 is its range reduction, which this does not use.
+// 8 issue slots per sin/cos pair instead of 24: the sine epilogue is FP32-issue-bound.
+__device__ __forceinline__ void mufu_sincos(float x, float& s, float& c) {
+    float kf = fmaf(x, 0.159154943f, 12582912.0f);          // round(x / 2pi)
+    kf -= 12582912.0f;
+    float r = fmaf(kf, -6.28125f, x);                       // 2pi = 6.28125 (8 bits: k*c1 exact) + 1.93530717e-3
+    r = fmaf(kf, -1.93530717e-3f, r);
+    s = __sinf(r);
+    c = __cosf(r);
+}
+template <int N>
+__device__ __forceinline__ void sincos_group_mufu(const float (&x)[N], float (&s)[N], float (&c)[N]) {
+    float big = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { mufu_sincos(x[i], s[i], c[i]); big = fmaxf(big, fabsf(x[i])); }
+    if (big > kSincosFastLimit) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const float2 r = slow_sincos(x[i]); s[i] = r.x; c[i] = r.y; }
+    }
+}
+
 template <typename T> __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

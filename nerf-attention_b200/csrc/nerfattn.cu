@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "siren_fp32.cuh"
 #include "siren_tc.cuh"
+#include "siren_chain.cuh"
 #include "decode.cuh"
 
 namespace na {
@@ -36,6 +37,7 @@ static bool env_flag(const char* name) {
     const char* v = getenv(name);
     return v && v[0] && strcmp(v, "0") != 0;
 }
+static bool chain_enabled() { return !env_flag("NERFATTN_NO_CHAIN"); }
 
 // ------------------------------------------------------------------ planning
 struct Group {
@@ -58,6 +60,11 @@ struct Group {
     float* losspart; int losspart_per_fit;
     __nv_bfloat16* wbf16;  // [nf][P] bf16 mirror of the weights (tensor path)
     tc::GroupMaps* maps;   // TMA descriptors (tensor path), host-side
+    // fused row-tile chain (siren_chain.cuh): forward + loss + dX chain in one kernel; cosb[l] then
+    // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch
+    bool use_chain;
+    __nv_bfloat16* chain_scratch;
+    chain::ChainMaps* cmaps;
 };
 
 struct Plan {
@@ -171,10 +178,14 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         }
         g.colpart = ar.take<float>(coff);
         g.xpart = ar.take<float>((size_t)g.nf * g.mtiles * g.H);
-        g.losspart_per_fit = bf ? tc::loss_partials_per_fit(g.N, g.D) : g.mtiles * ceil_div(g.D, 128);
+        g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
+        g.losspart_per_fit = g.use_chain ? chain::loss_partials_per_fit(g.N, g.H)
+                             : bf ? tc::loss_partials_per_fit(g.N, g.D) : g.mtiles * ceil_div(g.D, 128);
         g.losspart = ar.take<float>((size_t)g.nf * g.losspart_per_fit);
         g.wbf16 = bf ? ar.take<__nv_bfloat16>((size_t)g.nf * g.lm.P) : nullptr;
         g.maps = nullptr;
+        g.chain_scratch = g.use_chain ? ar.take<__nv_bfloat16>(chain::scratch_elems(g.H, g.L)) : nullptr;
+        g.cmaps = nullptr;
     }
     plan.bytes = ar.bytes();
     // stash per-fit unique ids in uniq_first_fit's tail: callers use fit_uniq via closure
@@ -364,7 +375,8 @@ extern "C" long long nerfattn_fit_launch_count(const na_fit_t* fits, int32_t nfi
     long long per_epoch = 1 /* tick */, fin = 0;
     for (const Group& g : plan.groups) {
         // layer0 + L fwd + out + (L+1) x (dW, dX) + Adam; the tensor path adds the layer-0 gradient kernel
-        per_epoch += 1 + g.L + 1 + 2 * (g.L + 1) + 1 + (precision == NA_PREC_BF16 ? 1 : 0);
+        if (g.use_chain) per_epoch += 1 + (g.L + 1) + 1 + 1;      // chain + dW per layer + layer-0 gradient + Adam
+        else per_epoch += 1 + g.L + 1 + 2 * (g.L + 1) + 1 + (precision == NA_PREC_BF16 ? 1 : 0);
         fin += 1 + g.L + 1 + 2;
         if (precision == NA_PREC_BF16) setup += 1;   // bf16 weight mirror
     }
@@ -473,13 +485,18 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
 
     // ---- tensor path set-up: TMA descriptors + initial bf16 weight mirror
     std::vector<tc::GroupMaps> maps(plan.groups.size());
+    std::vector<chain::ChainMaps> cmaps(plan.groups.size());
     if (precision == NA_PREC_BF16) {
         if ((rc = tc::configure_all())) return rc;
+        if ((rc = chain::configure_all())) return rc;
         for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
             Group& g = plan.groups[gi];
             g.maps = &maps[gi];
-            rc = tc::build_group_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.act, g.cosb, g.dz, g.dy, g.wbf16, *g.maps);
+            g.cmaps = &cmaps[gi];
+            rc = tc::build_group_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.act, g.cosb, g.dz, g.dy, g.wbf16, *g.maps,
+                                      g.use_chain ? g.cosb : nullptr);
             if (rc) return rc;
+            if (g.use_chain && (rc = chain::build_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.wbf16, g.act, g.cosb, g.dy, *g.cmaps))) return rc;
             tc::mirror_weights(g.d_recs, g.lm, g.nf, g.wbf16, stream);
             NA_LAUNCH_OK("mirror_weights");
         }
@@ -496,9 +513,13 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
             const Group& g = plan.groups[gi];
             if (precision == NA_PREC_FP32) fp32_epoch(g, plan, beta1, beta2, eps, s);
             else {
-                int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
-                                   g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                   g.losspart_per_fit, g.mtiles, s);
+                int r2 = g.use_chain
+                    ? chain::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, *g.cmaps, g.act, g.cosb, g.dy,
+                                   g.chain_scratch, g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
+                                   g.losspart_per_fit, g.mtiles, s)
+                    : tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
+                                g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
+                                g.losspart_per_fit, g.mtiles, s);
                 if (r2) return r2;
                 launch_adam(g, plan, beta1, beta2, eps, s);
             }
@@ -772,4 +793,21 @@ extern "C" int nerfattn_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, 
     if (!a_mn && b_mn) return tc::launch_bn<tc::kRaw, false, true>(bn, maps, a, stream);
     if (a_mn && !b_mn) return tc::launch_bn<tc::kRaw, true, false>(bn, maps, a, stream);
     return tc::launch_bn<tc::kRaw, true, true>(bn, maps, a, stream);
+}
+
+namespace na {
+__global__ void debug_sincos_kernel(const float* x, float* s, float* c, long long n, int mode) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a[1] = {x[i]}, sv[1], cv[1];
+    if (mode == 1) sincos_group_mufu(a, sv, cv); else sincos_group(a, sv, cv);
+    s[i] = sv[0]; c[i] = cv[0];
+}
+}  // namespace na
+
+extern "C" int nerfattn_debug_sincos(const float* x, float* s, float* c, int64_t n, int32_t mode, na_stream_t stream_) {
+    if (!x || !s || !c || n <= 0 || (mode != 0 && mode != 1)) { set_error("bad argument"); return NA_ERR_INVALID; }
+    debug_sincos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, s, c, (long long)n, mode);
+    NA_LAUNCH_OK("debug_sincos_kernel");
+    return NA_OK;
 }

@@ -1,0 +1,555 @@
+// Fused row-tile chain of the BF16 tensor path (sm_100a).
+//
+// The unfused path (siren_tc.cuh) runs one grouped GEMM kernel per layer and direction and
+// moves every activation through HBM between them: ~25 N*H*2 B per fit-epoch for `medium`,
+// which made the backward kernels HBM-bound while the sine epilogues were FP32-issue-bound,
+// one after the other.  Everything except dW is row-local, so here ONE persistent CTA takes a
+// 128-row tile of one fit through the whole chain
+//
+//   E0      h_0 = sin(w (x W0^T + b0))                          SIMT, positions never quantised
+//   S_l     z_l = h_{l-1} W_l^T  (tcgen05, A = h_{l-1} in smem)  -> h_l = sin(w (z_l + b_l))     l = 1..L
+//   OUT     y   = h_L Wf^T + bf                                  -> dY = 2 (y - t)/(N D), loss
+//   DXF     dh  = dY Wf          (A = dY in smem)                -> dz_L = dh * w cos_L
+//   DX_l    dh  = dz_l W_l       (A = dz_l in smem)              -> dz_{l-1} = dh * w cos_{l-1}  l = L..1
+//
+// (reference: siren.py:33-34,60-61,100-102).  The epilogue warps write each result straight
+// into shared memory in the 128B-swizzled K-major layout the next MMA reads as its A operand;
+// only the weights stream in (TMA, 3-stage ring).  The same buffer is what the dW GEMMs need
+// as h_l / dz_l, so one elected thread TMA-stores it to global (bf16) -- no LSU traffic for it.
+// dW contracts over all rows of a fit and stays a separate kernel.  cos_l goes to a small
+// per-CTA scratch that the same thread reads back in the backward half.
+//
+// Roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 4..19 epilogue.  For
+// H <= 256 two tiles ("slots") are in flight per CTA, each owned by its own set of 8 epilogue
+// warps: while one set runs its sine epilogue the tensor core runs the other slot's MMAs, and
+// with 4 epilogue warps per scheduler the TMEM / shared / L2 latencies of one warp hide under
+// the others (the first version alternated 8 warps over both slots and issued 28% of cycles).
+// TMEM: 2 x 256 accumulator columns.  H = 512 needs the whole TMEM and 128 KB of shared memory
+// for one tile: one slot, all 16 warps on it (a quarter of the columns each).
+#pragma once
+
+#include "siren_tc.cuh"
+
+namespace na {
+namespace chain {
+
+using namespace tc;
+
+constexpr int NCTRL = 4;                          // warpgroup 0: warp 0 = TMA, warp 1 = MMA, warps 2-3 idle
+constexpr int NEPI = 16;                          // epilogue warps 4..19
+constexpr int NTHREADS = (NCTRL + NEPI) * 32;     // 640
+constexpr int CHUNK_BYTES = BM * 64 * 2;          // one K-chunk of an A operand: 128 rows x 64 bf16
+constexpr int STAGE_BYTES = 256 * 64 * 2;         // one K-chunk of a weight operand: <= 256 x 64 bf16
+constexpr int STAGES = 3;
+constexpr int VEC_FLOATS = 512;
+
+template <int H> struct Cfg {
+    static constexpr int BN = (H >= 256) ? 256 : H;              // N of one hidden-layer MMA
+    static constexpr int NPARTS = H / BN;
+    static constexpr int NSLOT = (H <= 256) ? 2 : 1;
+    static constexpr int EPW = NEPI / NSLOT;                      // epilogue warps per slot
+    static constexpr int CG = EPW / 4;                            // column groups per slot
+    static constexpr int CW = H / CG;                             // columns per thread in a hidden step
+    static constexpr int NU = CW / 16;                            // 16-column units per thread
+    static constexpr int ACT_CHUNKS = ((H > 256) ? H : 256) / 64;   // dY (D <= 256) aliases the buffer
+    static constexpr int ACT_BYTES = ACT_CHUNKS * CHUNK_BYTES;
+    static constexpr int ACC_COLS = (H > 256) ? 512 : 256;
+    static constexpr int SMEM = NSLOT * ACT_BYTES + STAGES * STAGE_BYTES + VEC_FLOATS * 4 + 256;
+    static_assert(NSLOT * H <= VEC_FLOATS, "bias staging");
+    static_assert(NU >= 1 && CW % 16 == 0, "column split");
+};
+
+struct ChainArgs {
+    int N, D, L, nf, mtiles;
+    const FitRec* recs;
+    int w_off[kMaxLayers], b_off[kMaxLayers];
+    __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][128][H]
+    float* losspart; int losspart_per_fit; float loss_scale;
+    int dbg;                                // NERFATTN_CHAIN_DBG (profiling experiments only)
+    int sincos_mode;                        // bit 0: hidden layers, bit 1: layer 0 use the MUFU-core sincos (common.cuh)
+};
+// wk / wmn: weights of layers 1..L+1 as K-major (forward) and MN-major (backward) B operands (loads);
+// hout[l] / zout[l] / yout: h_l, dz_l [nf][N][H] and dY [nf][N][D] as 64 x 128 boxes (stores)
+struct ChainMaps {
+    CUtensorMap wk[kMaxHidden + 2]; CUtensorMap wmn[kMaxHidden + 2];
+    CUtensorMap hout[kMaxHidden + 1]; CUtensorMap zout[kMaxHidden + 1]; CUtensorMap yout;
+};
+
+inline bool shape_supported(int N, int D, int H, int L) {
+    return tc::shape_supported(N, D, H, L) && L >= 1;
+}
+inline int loss_partials_per_fit(int N, int H) { return (N / BM) * (H <= 256 ? NEPI / 2 : NEPI); }   // one per epilogue warp of the tile
+
+__device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// L2 residency control: the cos scratch is re-read by the same thread a few microseconds later
+// and then overwritten in place by the next tile (keep it: evict-last, and keep it out of the
+// small L1 that holds the layer-0 weights); targets are streamed past L1.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_global_256_hint(void* p, const uint32_t* v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+                 ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ld_global_256_hint(const void* p, uint32_t* v, uint64_t pol) {   // coherent (same-kernel data)
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_na_256(const void* p, uint32_t* v) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void set_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// 16 consecutive bf16 columns [col, col+16) of tile row r -> A-operand buffer (K-major, SWIZZLE_128B:
+// 64-column chunks of 128 rows x 128 B, 16-byte units XOR-ed with row % 8 -- the TMA layout)
+__device__ __forceinline__ void act_store16(uint32_t act_u32, int r, int col, const uint32_t (&pk)[8]) {
+    const uint32_t rowaddr = act_u32 + (uint32_t)(col >> 6) * CHUNK_BYTES + (uint32_t)r * 128;
+    const int u0 = (col & 63) >> 3;
+    st_shared_128(rowaddr + (uint32_t)((u0 ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_128(rowaddr + (uint32_t)(((u0 + 1) ^ (r & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+}
+
+// what MMA step s (1-based; step 0 is the SIMT layer 0) contracts
+struct Step { int layer; int mn; int kch; int n; int nparts; };
+template <int H>
+__device__ __forceinline__ Step step_info(int s, int L, int D) {
+    using C = Cfg<H>;
+    Step st;
+    if (s <= L) { st.layer = s; st.mn = 0; st.kch = H / 64; st.n = C::BN; st.nparts = C::NPARTS; }
+    else if (s == L + 1) { st.layer = L + 1; st.mn = 0; st.kch = H / 64; st.n = D; st.nparts = 1; }
+    else if (s == L + 2) { st.layer = L + 1; st.mn = 1; st.kch = D / 64; st.n = C::BN; st.nparts = C::NPARTS; }
+    else { st.layer = 2 * L + 3 - s; st.mn = 1; st.kch = H / 64; st.n = C::BN; st.nparts = C::NPARTS; }
+    return st;
+}
+
+template <bool MUFU>
+__device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], float (&c)[8]) {
+    if (MUFU) sincos_group_mufu(x, s, c); else sincos_group(x, s, c);
+}
+
+template <int H>
+__global__ void __launch_bounds__(NTHREADS, 1)
+chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
+    using C = Cfg<H>;
+    constexpr int NSLOT = C::NSLOT;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_ring = smem + NSLOT * C::ACT_BYTES;
+    float* vecs = reinterpret_cast<float*>(smem_ring + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(vecs + VEC_FLOATS);
+    uint64_t* full = bars;                       // [STAGES]  weights landed
+    uint64_t* empty = bars + STAGES;             // [STAGES]  MMAs that read the stage retired
+    uint64_t* acc_full = bars + 2 * STAGES;      // [2]       accumulator of the slot complete
+    uint64_t* act_ready = bars + 2 * STAGES + 2; // [2]       A operand of the slot written, accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = g.L, D = g.D;
+    const int total_tiles = g.nf * g.mtiles;
+    const int nsteps = 2 * L + 3;                // step 0 (layer 0) + 2L+2 MMA steps
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) { printf("nerfattn: chain smem base not 1024-aligned\n"); __trap(); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer: weights only
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int round = 0;; ++round) {
+                const int t0 = blockIdx.x + round * NSLOT * gridDim.x;
+                if (t0 >= total_tiles) break;
+                for (int s = 1; s < nsteps; ++s) {
+                    const Step st = step_info<H>(s, L, D);
+                    const CUtensorMap* map = st.mn ? &maps.wmn[st.layer] : &maps.wk[st.layer];
+                    const uint32_t tx = (uint32_t)st.n * 128u;
+                    for (int slot = 0; slot < NSLOT; ++slot) {
+                        const int tile = t0 + slot * gridDim.x;
+                        if (tile >= total_tiles) break;
+                        const int fit = tile / g.mtiles;
+                        for (int np = 0; np < st.nparts; ++np)
+                            for (int kc = 0; kc < st.kch; ++kc) {
+                                mbar_wait(&empty[stage], phase ^ 1);
+                                mbar_expect_tx(&full[stage], tx);
+                                uint8_t* sb = smem_ring + stage * STAGE_BYTES;
+                                if (!st.mn) tma_load_3d(sb, map, &full[stage], kc * 64, np * 256, fit);
+                                else
+                                    for (int i = 0; i < st.n / 64; ++i)
+                                        tma_load_3d(sb + i * 8192, map, &full[stage], np * 256 + i * 64, kc * 64, fit);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        int stage = 0; uint32_t phase = 0;
+        uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot]
+        for (int round = 0;; ++round) {
+            const int t0 = blockIdx.x + round * NSLOT * gridDim.x;
+            if (t0 >= total_tiles) break;
+            for (int s = 1; s < nsteps; ++s) {
+                const Step st = step_info<H>(s, L, D);
+                const uint32_t idesc = make_idesc(st.n, false, st.mn != 0);
+                const uint32_t b_lbo = st.mn ? 8192u : 0u;
+                const uint32_t b_kadv = st.mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+                for (int slot = 0; slot < NSLOT; ++slot) {
+                    if (t0 + slot * (int)gridDim.x >= total_tiles) break;
+                    mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
+                    rdy_phase ^= 1u << slot;
+                    tc_fence_after();
+                    const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
+                    for (int np = 0; np < st.nparts; ++np) {
+                        const uint32_t d_tmem = tmem_base + slot * C::ACC_COLS + np * 256;
+                        for (int kc = 0; kc < st.kch; ++kc) {
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t adesc0 = make_desc(act_u32 + kc * CHUNK_BYTES, 0, 1024);
+                                const uint64_t bdesc0 = make_desc(smem_u32(smem_ring + stage * STAGE_BYTES), b_lbo, 1024);
+#pragma unroll
+                                for (int k = 0; k < 64 / UMMA_K; ++k)
+                                    tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
+                                                (kc > 0 || k > 0) ? 1u : 0u);
+                                tc_commit(&empty[stage]);
+                                if (np == st.nparts - 1 && kc == st.kch - 1) tc_commit(&acc_full[slot]);
+                            }
+                            __syncwarp();
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= NCTRL) {
+        // ===================================================== epilogue warps: one set per slot
+        const int e = warp - NCTRL;
+        const int slot = e / C::EPW;                  // the slot this warp's set owns
+        const int ei = e % C::EPW;
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int cg = ei >> 2;                       // column group inside the slot
+        const int r = q * 32 + lane;                  // row inside the tile
+        const int st_tid = ei * 32 + lane;            // thread index inside the set
+        const bool leader = st_tid == 0;
+        const int bar_id = 1 + slot;
+        constexpr int SET_THREADS = C::EPW * 32;
+        constexpr int NU = C::NU;
+        constexpr int PFD = (NU < 4) ? NU : 4;        // cos units in flight in the backward epilogue
+        const int col0 = cg * C::CW;
+        float* const vec = vecs + slot * H;
+        const uint64_t pol_keep = policy_evict_last();
+        const bool mufu_hidden = (g.sincos_mode & 1) != 0, mufu_l0 = (g.sincos_mode & 2) != 0;
+        const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
+        const uint32_t t_row = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + col0;
+        __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H) + (size_t)r * H + col0;
+        uint32_t acc_phase = 0;
+        for (int round = 0;; ++round) {
+            const int tile = blockIdx.x + (round * NSLOT + slot) * gridDim.x;
+            if (tile >= total_tiles) break;
+            const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
+            const FitRec* rec = &g.recs[fit];
+            const int row = mt * BM + r;
+            const float omega = rec->omega;
+            for (int s = 0; s < nsteps; ++s) {
+                // the TMA store of the previous step must have read the operand buffer before it is overwritten
+                if (leader) tma_store_wait_read();
+                const CUtensorMap* omap;
+                int ochunks = H / 64;
+                if (s == 0) {
+                    set_bar(bar_id, SET_THREADS);
+                    omap = &maps.hout[0];
+                    // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
+                    const float x = __ldg(rec->pos + row);
+                    const float* w0 = rec->params + g.w_off[0] + col0;
+                    const float* b0 = rec->params + g.b_off[0] + col0;
+                    float4 wn[2], bn[2];                         // weights / biases of the next 8 columns
+                    wn[0] = __ldg(reinterpret_cast<const float4*>(w0)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0) + 1);
+                    bn[0] = __ldg(reinterpret_cast<const float4*>(b0)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0) + 1);
+#pragma unroll 1
+                    for (int u = 0; u < NU; ++u) {
+                        uint32_t so[8], co[8];
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+                            float arg[8], sn[8], cs[8];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                arg[4 * j] = omega * fmaf(x, wn[j].x, bn[j].x); arg[4 * j + 1] = omega * fmaf(x, wn[j].y, bn[j].y);
+                                arg[4 * j + 2] = omega * fmaf(x, wn[j].z, bn[j].z); arg[4 * j + 3] = omega * fmaf(x, wn[j].w, bn[j].w);
+                            }
+                            const int nxt = (u * 2 + gi + 1 < NU * 2) ? (u * 2 + gi + 1) * 8 : 0;
+                            wn[0] = __ldg(reinterpret_cast<const float4*>(w0 + nxt)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0 + nxt) + 1);
+                            bn[0] = __ldg(reinterpret_cast<const float4*>(b0 + nxt)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0 + nxt) + 1);
+                            if (mufu_l0) sincos8<true>(arg, sn, cs); else sincos8<false>(arg, sn, cs);
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                so[(gi * 8 + j) / 2] = pack_bf16(sn[j], sn[j + 1]);
+                                co[(gi * 8 + j) / 2] = pack_bf16(cs[j], cs[j + 1]);
+                            }
+                        }
+                        act_store16(act_u32, r, col0 + u * 16, so);
+                        st_global_256_hint(scr + u * 16, co, pol_keep);
+                    }
+                } else if (s <= L) {
+                    // ---------------- hidden sine layer s
+                    omap = &maps.hout[s];
+                    {
+                        const float* b = rec->params + g.b_off[s];
+                        for (int j = st_tid; j < H; j += SET_THREADS) vec[j] = omega * __ldg(b + j);
+                    }
+                    set_bar(bar_id, SET_THREADS);
+                    mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    tc_fence_after();
+                    __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
+                    uint32_t v[16];
+                    tmem_ld16(t_row, v);
+#pragma unroll 1
+                    for (int u = 0; u < NU; ++u) {
+                        float arg[16];
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(vec + col0 + u * 16 + j);
+                            arg[j] = fmaf(__uint_as_float(v[j]), omega, bb.x);
+                            arg[j + 1] = fmaf(__uint_as_float(v[j + 1]), omega, bb.y);
+                            arg[j + 2] = fmaf(__uint_as_float(v[j + 2]), omega, bb.z);
+                            arg[j + 3] = fmaf(__uint_as_float(v[j + 3]), omega, bb.w);
+                        }
+                        if (u + 1 < NU) tmem_ld16(t_row + (u + 1) * 16, v);      // in flight during the sincos below
+                        uint32_t so[8], co[8];
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+                            float a8[8], sn[8], cs[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a8[j] = arg[gi * 8 + j];
+                            if (mufu_hidden) sincos8<true>(a8, sn, cs); else sincos8<false>(a8, sn, cs);
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                so[(gi * 8 + j) / 2] = pack_bf16(sn[j], sn[j + 1]);
+                                co[(gi * 8 + j) / 2] = pack_bf16(cs[j], cs[j + 1]);
+                            }
+                        }
+                        act_store16(act_u32, r, col0 + u * 16, so);
+                        st_global_256_hint(cdst + u * 16, co, pol_keep);
+                    }
+                } else if (s == L + 1) {
+                    // ---------------- output layer: dY = 2 (y - t) / (N D), loss partial (siren.py:101)
+                    omap = &maps.yout; ochunks = D / 64;
+                    {
+                        const float* b = rec->params + g.b_off[L + 1];
+                        for (int j = st_tid; j < D; j += SET_THREADS) vec[j] = __ldg(b + j);
+                    }
+                    set_bar(bar_id, SET_THREADS);
+                    const int ow = D / C::CG;                    // output columns of this thread
+                    const int ocol0 = cg * ow;
+                    const float* tn = rec->tnorm + (size_t)row * D + ocol0;
+                    uint32_t tt[16];
+                    ld_global_nc_na_256(tn, &tt[0]); ld_global_nc_na_256(tn + 8, &tt[8]);
+                    mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    tc_fence_after();
+                    const uint32_t t_out = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + ocol0;
+                    float sq = 0.f;
+                    uint32_t v[16];
+#pragma unroll 1
+                    for (int u = 0; u < ow / 16; ++u) {
+                        tmem_ld16(t_out + u * 16, v);
+                        tmem_ld_wait();
+                        uint32_t dout[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(vec + ocol0 + u * 16 + j);
+                            const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - __uint_as_float(tt[j + 0]);
+                            const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - __uint_as_float(tt[j + 1]);
+                            const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - __uint_as_float(tt[j + 2]);
+                            const float e3 = (__uint_as_float(v[j + 3]) + bb.w) - __uint_as_float(tt[j + 3]);
+                            sq = fmaf(e0, e0, sq); sq = fmaf(e1, e1, sq); sq = fmaf(e2, e2, sq); sq = fmaf(e3, e3, sq);
+                            dout[j / 2] = pack_bf16(e0 * g.loss_scale, e1 * g.loss_scale);
+                            dout[j / 2 + 1] = pack_bf16(e2 * g.loss_scale, e3 * g.loss_scale);
+                        }
+                        if ((u + 1) * 16 < ow) { ld_global_nc_na_256(tn + (u + 1) * 16, &tt[0]); ld_global_nc_na_256(tn + (u + 1) * 16 + 8, &tt[8]); }
+                        act_store16(act_u32, r, ocol0 + u * 16, dout);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0) g.losspart[(size_t)fit * g.losspart_per_fit + mt * C::EPW + ei] = sq;
+                } else {
+                    // ---------------- backward: dz_{lp} = (dz_{lp+1} W_{lp+1}) * w cos_{lp}
+                    const int lp = 2 * L + 2 - s;                // L, L-1, .., 0
+                    omap = &maps.zout[lp];
+                    set_bar(bar_id, SET_THREADS);
+                    const __nv_bfloat16* csrc = scr + (size_t)lp * (BM * H);
+                    uint32_t cc[PFD][8];
+#pragma unroll
+                    for (int p = 0; p < PFD; ++p) ld_global_256_hint(csrc + p * 16, cc[p], pol_keep);
+                    mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    tc_fence_after();
+                    uint32_t va[16], vb[16];
+                    tmem_ld16(t_row, va);
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        uint32_t (&v)[16] = (u & 1) ? vb : va;
+                        tmem_ld_wait();
+                        if (u + 1 < NU) tmem_ld16(t_row + (u + 1) * 16, (u & 1) ? va : vb);
+                        uint32_t dout[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            float c0, c1;
+                            unpack_bf16(cc[u % PFD][t], c0, c1);
+                            dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * c0),
+                                                __uint_as_float(v[2 * t + 1]) * (omega * c1));
+                        }
+                        if (u + PFD < NU) ld_global_256_hint(csrc + (u + PFD) * 16, cc[u % PFD], pol_keep);
+                        act_store16(act_u32, r, col0 + u * 16, dout);
+                    }
+                }
+                // operand buffer complete: publish it to the tensor core (next MMA) and to global (dW operand)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
+                tc_fence_before();
+                set_bar(bar_id, SET_THREADS);
+                if (leader) {
+                    if (s < nsteps - 1) mbar_arrive(&act_ready[slot]);
+                    if (!(g.dbg & 1)) {
+                        for (int kc = 0; kc < ochunks; ++kc)
+                            tma_store_3d(omap, smem + slot * C::ACT_BYTES + kc * CHUNK_BYTES, kc * 64, mt * BM, fit);
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA retires
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------ host
+inline size_t scratch_elems(int H, int L) {
+    const int nslot = (H <= 256) ? 2 : 1;
+    return (size_t)num_sms() * nslot * (L + 1) * BM * H;
+}
+
+inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16,
+                      void* const* act, void* const* dzs, void* dy, ChainMaps& m) {
+    int rc;
+    for (int l = 0; l <= L; ++l) {
+        if ((rc = make_operand_map(&m.hout[l], act[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
+        if ((rc = make_operand_map(&m.zout[l], dzs[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
+    }
+    if ((rc = make_operand_map(&m.yout, dy, N, D, nf, (size_t)N * D, false, BM))) return rc;
+    for (int l = 1; l <= L + 1; ++l) {
+        const int rows = lm.out_dim[l];
+        const int box = (l == L + 1) ? D : (H >= 256 ? 256 : H);
+        if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], rows, H, nf, lm.P, false, box))) return rc;
+        if ((rc = make_operand_map(&m.wmn[l], wbf16 + lm.w_off[l], rows, H, nf, lm.P, true, 0))) return rc;
+    }
+    return NA_OK;
+}
+
+template <int H>
+inline int launch_h(const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
+    const int tiles = a.nf * a.mtiles;
+    const int grid = std::min(tiles, num_sms());
+    chain_kernel<H><<<grid, NTHREADS, Cfg<H>::SMEM, s>>>(maps, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
+    return NA_OK;
+}
+inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
+    switch (H) {
+        case 64: return launch_h<64>(maps, a, s);
+        case 128: return launch_h<128>(maps, a, s);
+        case 256: return launch_h<256>(maps, a, s);
+        case 512: return launch_h<512>(maps, a, s);
+        default: set_error("chain: unsupported H %d", H); return NA_ERR_UNSUPPORTED;
+    }
+}
+
+// NERFATTN_SINCOS: 0 = polynomial everywhere, 1 = MUFU core in the hidden layers (default: their
+// results are rounded to bf16 at once), 3 = MUFU core in layer 0 too
+inline int sincos_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("NERFATTN_SINCOS"); mode = e ? (int)strtol(e, nullptr, 0) & 3 : 1; }
+    return mode;
+}
+
+// One training epoch of one group: the chain, then the dW GEMMs (contraction over all rows of a fit)
+// and the layer-0 gradient; Adam follows in the caller.
+inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const GroupMaps& m,
+                 const ChainMaps& cm, void* const* act, void* const* dzs, void* dy, __nv_bfloat16* scratch,
+                 float* gradpart, float* colpart, const size_t* colpart_layer_off, float* xpart, float* losspart,
+                 int losspart_per_fit, int mtiles, cudaStream_t s) {
+    int rc;
+    ChainArgs a{};
+    a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
+    for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
+    (void)act; (void)dy;                       // written through the TMA store maps in `cm`
+    a.scratch = scratch;
+    a.losspart = losspart; a.losspart_per_fit = losspart_per_fit;
+    a.loss_scale = 2.0f / ((float)N * (float)D);
+    a.sincos_mode = sincos_mode();
+    { const char* e = getenv("NERFATTN_CHAIN_DBG"); a.dbg = e ? atoi(e) : 0; }
+    if ((rc = launch(H, cm, a, s))) return rc;
+    TcArgs base{};
+    base.nb = nf; base.recs = recs;
+    for (int l = L + 1; l >= 1; --l) {
+        const int width = lm.out_dim[l];
+        TcArgs w = base;
+        w.M = width; w.N = H; w.K = N;
+        w.fout = gradpart; w.fout_fit = lm.P; w.fout_off = lm.w_off[l]; w.ldf = H;
+        w.biasgrad = colpart + colpart_layer_off[l]; w.biasgrad_fit = width;
+        if ((rc = launch_bn<kDw, true, true>(dw_bn(H), m.dw[l], w, s))) return rc;
+    }
+    layer0_grad_kernel<<<dim3(mtiles, nf), 256, 0, s>>>(recs, (const __nv_bfloat16*)dzs[0], (size_t)N * H, N, H, mtiles,
+                                                        xpart, colpart + colpart_layer_off[0]);
+    return NA_OK;
+}
+
+inline int configure_all() {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
+        acc(cudaFuncSetAttribute(chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<512>::SMEM));
+    });
+    if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(chain smem) failed: %s", cudaGetErrorString(err)); return NA_ERR_CUDA; }
+    return NA_OK;
+}
+
+}  // namespace chain
+}  // namespace na

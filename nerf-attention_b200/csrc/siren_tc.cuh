@@ -577,8 +577,10 @@ struct GroupMaps {
 inline int hidden_bn(int H) { return H >= 256 ? 256 : H; }
 inline int dw_bn(int H) { return H >= 128 ? 128 : 64; }
 
+// `dz_per_layer` (chain mode): dz_l has its own array per layer instead of the two ping-pong buffers
 inline int build_group_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, void* const* act, void* const* cosb,
-                            void* const* dz, void* dy, __nv_bfloat16* wbf16, GroupMaps& m) {
+                            void* const* dz, void* dy, __nv_bfloat16* wbf16, GroupMaps& m,
+                            void* const* dz_per_layer = nullptr) {
     (void)cosb;
     const size_t nh = (size_t)N * H, nd = (size_t)N * D;
     int rc;
@@ -590,7 +592,7 @@ inline int build_group_maps(int N, int D, int H, int L, int nf, const LayerMap& 
     if ((rc = make_operand_map(&m.out.b, wbf16 + lm.w_off[L + 1], D, H, nf, lm.P, false, out_bn(D)))) return rc;
     for (int l = L + 1; l >= 1; --l) {
         const int width = lm.out_dim[l];
-        const void* dzl = (l == L + 1) ? dy : dz[l & 1];
+        const void* dzl = (l == L + 1) ? dy : (dz_per_layer ? dz_per_layer[l] : dz[l & 1]);
         const size_t dz_fit = (l == L + 1) ? nd : nh;
         // dx: A = dz_l [N x width] K-major, B = W_l [width x H] MN-major
         if ((rc = make_operand_map(&m.dx[l].a, dzl, N, width, nf, dz_fit, false, BM))) return rc;

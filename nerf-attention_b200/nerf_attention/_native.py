@@ -11,7 +11,7 @@ import ctypes
 import os
 from pathlib import Path
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'bf16': PREC_BF16}
@@ -61,6 +61,7 @@ _SIGNATURES = {
                                      c_void_p]),
     'nerfattn_debug_gemm_bf16': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_void_p]),
+    'nerfattn_debug_sincos': (c_int32, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
