@@ -260,8 +260,12 @@ static void launch_adam(const Group& g, const Plan& plan, double beta1, double b
     a.loss_inv_count = 1.0f / ((float)g.N * (float)g.D);
     a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
     a.wbf16 = g.wbf16; a.wbf16_fit = g.lm.P;
-    dim3 grid(ceil_div(g.lm.P, 1024), g.nf);
-    f32::adam_kernel<<<grid, 256, 0, s>>>(a);
+    // 64-thread blocks (3 K registers, no shared memory): small enough to be co-scheduled on SMs whose
+    // registers and shared memory are almost entirely held by another group's chain CTA, so this
+    // HBM-bound update overlaps that group's issue-bound kernel instead of waiting for free SMs
+    const int adam_threads = env_flag("NERFATTN_ADAM256") ? 256 : 64;
+    dim3 grid(ceil_div(g.lm.P, adam_threads * 4), g.nf);
+    f32::adam_kernel<<<grid, adam_threads, 0, s>>>(a);
 }
 
 // one training epoch of one group, fp32 SIMT path
@@ -620,7 +624,8 @@ static void infer_plan(const na_fit_t* m, int n, int precision, bool decode, voi
     if (decode) {
         p.u = ar.take<float>((size_t)n * g.H);
         p.c0 = ar.take<float>(n);
-        p.nparts = bf ? (g.H / tc::hidden_bn(g.H)) * 2 : ceil_div(g.H, f32::BN);
+        const bool dchain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
+        p.nparts = dchain ? chain::decode_parts(g.H) : bf ? (g.H / tc::hidden_bn(g.H)) * 2 : ceil_div(g.H, f32::BN);
         p.dotpart = ar.take<float>((size_t)n * p.nparts * g.N);
     }
     p.bytes = ar.bytes();
@@ -721,6 +726,12 @@ extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void*
         a.dotvec = p.u; a.dotvec_fit = g.H;
         a.dotpart = p.dotpart; a.dotpart_fit = (size_t)p.nparts * g.N;
         launch_sgemm<f32::kFwdDot, true, true>(a, n, 1, stream);
+    } else if (chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L)) {
+        // fused forward chain: layer 0, the hidden layers and the u . sin(.) reduction in one kernel
+        if ((rc = chain::configure_all())) return rc;
+        chain::ChainMaps cm;
+        if ((rc = chain::build_fwd_maps(g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
+        if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, p.u, p.dotpart, stream))) return rc;
     } else {
         const int bn = tc::hidden_bn(g.H);
         {

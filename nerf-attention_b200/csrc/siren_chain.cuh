@@ -41,7 +41,6 @@ constexpr int NTHREADS = (NCTRL + NEPI) * 32;     // 640
 constexpr int CHUNK_BYTES = BM * 64 * 2;          // one K-chunk of an A operand: 128 rows x 64 bf16
 constexpr int STAGE_BYTES = 256 * 64 * 2;         // one K-chunk of a weight operand: <= 256 x 64 bf16
 constexpr int STAGES = 3;
-constexpr int VEC_FLOATS = 512;
 
 template <int H> struct Cfg {
     static constexpr int BN = (H >= 256) ? 256 : H;              // N of one hidden-layer MMA
@@ -54,8 +53,7 @@ template <int H> struct Cfg {
     static constexpr int ACT_CHUNKS = ((H > 256) ? H : 256) / 64;   // dY (D <= 256) aliases the buffer
     static constexpr int ACT_BYTES = ACT_CHUNKS * CHUNK_BYTES;
     static constexpr int ACC_COLS = (H > 256) ? 512 : 256;
-    static constexpr int SMEM = NSLOT * ACT_BYTES + STAGES * STAGE_BYTES + VEC_FLOATS * 4 + 256;
-    static_assert(NSLOT * H <= VEC_FLOATS, "bias staging");
+    static constexpr int SMEM = NSLOT * ACT_BYTES + STAGES * STAGE_BYTES + 256;
     static_assert(NU >= 1 && CW % 16 == 0, "column split");
 };
 
@@ -65,6 +63,7 @@ struct ChainArgs {
     int w_off[kMaxLayers], b_off[kMaxLayers];
     __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][128][H]
     float* losspart; int losspart_per_fit; float loss_scale;
+    const float* dotvec; float* dotpart;    // forward-only (decode): u [nf][H] fp32, partial scores [nf][CG][N]
     int dbg;                                // NERFATTN_CHAIN_DBG (profiling experiments only)
     int sincos_mode;                        // bit 0: hidden layers, bit 1: layer 0 use the MUFU-core sincos (common.cuh)
 };
@@ -115,6 +114,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {      // bytes: multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void set_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -146,15 +152,18 @@ __device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], floa
     if (MUFU) sincos_group_mufu(x, s, c); else sincos_group(x, s, c);
 }
 
-template <int H>
+// FWD = false: the training chain above.  FWD = true: forward only, for the fused decode
+// (evaluate.py:173-242 times this reconstruction): E0, S_1..S_L, and instead of materialising K the
+// last sine epilogue reduces u . sin(.) per position, u = Wf^T (q * std) (decode.cuh) -- no cos, no
+// global stores except one partial score per position and column group.
+template <int H, bool FWD>
 __global__ void __launch_bounds__(NTHREADS, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     using C = Cfg<H>;
     constexpr int NSLOT = C::NSLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_ring = smem + NSLOT * C::ACT_BYTES;
-    float* vecs = reinterpret_cast<float*>(smem_ring + STAGES * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(vecs + VEC_FLOATS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + STAGES * STAGE_BYTES);
     uint64_t* full = bars;                       // [STAGES]  weights landed
     uint64_t* empty = bars + STAGES;             // [STAGES]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * STAGES;      // [2]       accumulator of the slot complete
@@ -164,12 +173,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = g.L, D = g.D;
     const int total_tiles = g.nf * g.mtiles;
-    const int nsteps = 2 * L + 3;                // step 0 (layer 0) + 2L+2 MMA steps
+    const int nsteps = FWD ? L + 1 : 2 * L + 3;  // step 0 (layer 0) + the MMA steps
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) { printf("nerfattn: chain smem base not 1024-aligned\n"); __trap(); }
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], C::EPW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -181,10 +190,38 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // register reallocation (sm_90+): the two control warps need few registers, the epilogue warps want more
+    // than the 96 a 640-thread CTA gets by default
+    if (warp < NCTRL) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ===================================================== TMA producer: weights only
+        // The ring holds 96 KB, one hidden step reads 128 KB, and the 16 CTAs working on a fit ask for
+        // the same chunk at the same moment: without help every step waits one DRAM latency for
+        // its last chunk.  So the weights of step s+1 are pulled into L2 while step s is loaded.
         if (elect_one()) {
+            auto prefetch_step = [&](int s, int fit) {
+                const Step st = step_info<H>(s, L, D);
+                const CUtensorMap* map = st.mn ? &maps.wmn[st.layer] : &maps.wk[st.layer];
+                for (int np = 0; np < st.nparts; ++np)
+                    for (int kc = 0; kc < st.kch; ++kc) {
+                        if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256, fit);
+                        else
+                            for (int i = 0; i < st.n / 64; ++i) tma_prefetch_3d(map, np * 256 + i * 64, kc * 64, fit);
+                    }
+            };
             int stage = 0; uint32_t phase = 0;
+            // the 128 x D fp32 target rows of a tile are contiguous: pull them into L2 when the tile starts
+            // (the OUT epilogue, half a tile later, otherwise walks them at DRAM latency)
+            auto prefetch_targets = [&](int tile) {
+                if (FWD) return;
+                const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
+                l2_prefetch_bulk(g.recs[fit].tnorm + (size_t)mt * BM * D, (uint32_t)(BM * D * 4));
+            };
+            for (int slot = 0; slot < NSLOT; ++slot) {
+                const int tile = blockIdx.x + slot * gridDim.x;
+                if (tile < total_tiles) { prefetch_step(1, tile / g.mtiles); prefetch_targets(tile); }
+            }
             for (int round = 0;; ++round) {
                 const int t0 = blockIdx.x + round * NSLOT * gridDim.x;
                 if (t0 >= total_tiles) break;
@@ -196,6 +233,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         const int tile = t0 + slot * gridDim.x;
                         if (tile >= total_tiles) break;
                         const int fit = tile / g.mtiles;
+                        if (s + 1 < nsteps) prefetch_step(s + 1, fit);
+                        else {
+                            const int ntile = tile + NSLOT * gridDim.x;
+                            if (ntile < total_tiles) {
+                                if (ntile / g.mtiles != fit) prefetch_step(1, ntile / g.mtiles);
+                                prefetch_targets(ntile);
+                            }
+                        }
                         for (int np = 0; np < st.nparts; ++np)
                             for (int kc = 0; kc < st.kch; ++kc) {
                                 mbar_wait(&empty[stage], phase ^ 1);
@@ -212,29 +257,48 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
+        // ===================================================== MMA issuer (+ TMA stores of the finished operand buffers)
+        // Step s consumes what the epilogue wrote in step s-1: it first TMA-stores that buffer to
+        // global (h_l / dY / dz_l, the dW operands), then contracts it.  Step `nsteps` only stores
+        // (dz_0) and hands the buffer back.  acc_full[slot] = accumulator complete AND buffer free.
         int stage = 0; uint32_t phase = 0;
         uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot]
         for (int round = 0;; ++round) {
             const int t0 = blockIdx.x + round * NSLOT * gridDim.x;
             if (t0 >= total_tiles) break;
-            for (int s = 1; s < nsteps; ++s) {
-                const Step st = step_info<H>(s, L, D);
+            for (int s = 1; s <= (FWD ? nsteps - 1 : nsteps); ++s) {
+                const Step st = step_info<H>(s < nsteps ? s : 1, L, D);
                 const uint32_t idesc = make_idesc(st.n, false, st.mn != 0);
                 const uint32_t b_lbo = st.mn ? 8192u : 0u;
                 const uint32_t b_kadv = st.mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+                // what the epilogue produced in step s-1
+                const int ps = s - 1;
+                const CUtensorMap* omap = (ps <= L) ? &maps.hout[ps] : (ps == L + 1) ? &maps.yout : &maps.zout[2 * L + 2 - ps];
+                const int ochunks = (ps == L + 1) ? D / 64 : H / 64;
                 for (int slot = 0; slot < NSLOT; ++slot) {
-                    if (t0 + slot * (int)gridDim.x >= total_tiles) break;
+                    const int tile = t0 + slot * (int)gridDim.x;
+                    if (tile >= total_tiles) break;
+                    const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
                     mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
                     rdy_phase ^= 1u << slot;
                     tc_fence_after();
-                    const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
+                    uint8_t* const act = smem + slot * C::ACT_BYTES;
+                    if (!FWD && lane == 0 && !(g.dbg & 1)) {
+                        for (int kc = 0; kc < ochunks; ++kc) tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, mt * BM, fit);
+                        tma_store_commit();
+                    }
+                    if (s == nsteps) {
+                        if (lane == 0) { tma_store_wait_read(); mbar_arrive(&acc_full[slot]); }
+                        __syncwarp();
+                        continue;
+                    }
+                    const uint32_t act_u32 = smem_u32(act);
                     for (int np = 0; np < st.nparts; ++np) {
                         const uint32_t d_tmem = tmem_base + slot * C::ACC_COLS + np * 256;
                         for (int kc = 0; kc < st.kch; ++kc) {
                             mbar_wait(&full[stage], phase);
                             tc_fence_after();
-                            if (elect_one()) {
+                            if (lane == 0) {
                                 const uint64_t adesc0 = make_desc(act_u32 + kc * CHUNK_BYTES, 0, 1024);
                                 const uint64_t bdesc0 = make_desc(smem_u32(smem_ring + stage * STAGE_BYTES), b_lbo, 1024);
 #pragma unroll
@@ -242,7 +306,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                                     tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
                                                 (kc > 0 || k > 0) ? 1u : 0u);
                                 tc_commit(&empty[stage]);
-                                if (np == st.nparts - 1 && kc == st.kch - 1) tc_commit(&acc_full[slot]);
+                                if (np == st.nparts - 1 && kc == st.kch - 1) {
+                                    if (!FWD) tma_store_wait_read();  // the store has read the buffer long before the MMAs retire
+                                    tc_commit(&acc_full[slot]);
+                                }
                             }
                             __syncwarp();
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -251,7 +318,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 }
             }
         }
-    } else if (warp >= NCTRL) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA retires
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===================================================== epilogue warps: one set per slot
         const int e = warp - NCTRL;
         const int slot = e / C::EPW;                  // the slot this warp's set owns
@@ -259,14 +329,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int cg = ei >> 2;                       // column group inside the slot
         const int r = q * 32 + lane;                  // row inside the tile
-        const int st_tid = ei * 32 + lane;            // thread index inside the set
-        const bool leader = st_tid == 0;
-        const int bar_id = 1 + slot;
-        constexpr int SET_THREADS = C::EPW * 32;
         constexpr int NU = C::NU;
         constexpr int PFD = (NU < 4) ? NU : 4;        // cos units in flight in the backward epilogue
         const int col0 = cg * C::CW;
-        float* const vec = vecs + slot * H;
         const uint64_t pol_keep = policy_evict_last();
         const bool mufu_hidden = (g.sincos_mode & 1) != 0, mufu_l0 = (g.sincos_mode & 2) != 0;
         const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
@@ -281,13 +346,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             const int row = mt * BM + r;
             const float omega = rec->omega;
             for (int s = 0; s < nsteps; ++s) {
-                // the TMA store of the previous step must have read the operand buffer before it is overwritten
-                if (leader) tma_store_wait_read();
-                const CUtensorMap* omap;
-                int ochunks = H / 64;
                 if (s == 0) {
-                    set_bar(bar_id, SET_THREADS);
-                    omap = &maps.hout[0];
+                    // the buffer is free once the MMA warp has stored the previous tile's dz_0
+                    if (!FWD && round > 0) { mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1; }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
                     const float x = __ldg(rec->pos + row);
                     const float* w0 = rec->params + g.w_off[0] + col0;
@@ -317,34 +378,36 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             }
                         }
                         act_store16(act_u32, r, col0 + u * 16, so);
-                        st_global_256_hint(scr + u * 16, co, pol_keep);
+                        if (!FWD) st_global_256_hint(scr + u * 16, co, pol_keep);
                     }
                 } else if (s <= L) {
                     // ---------------- hidden sine layer s
-                    omap = &maps.hout[s];
-                    {
-                        const float* b = rec->params + g.b_off[s];
-                        for (int j = st_tid; j < H; j += SET_THREADS) vec[j] = omega * __ldg(b + j);
-                    }
-                    set_bar(bar_id, SET_THREADS);
+                    const float* bsrc = rec->params + g.b_off[s] + col0;
+                    float4 bn[4];                                // bias of the next 16 columns (L1-resident)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc) + j);
                     mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
                     tc_fence_after();
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
                     uint32_t v[16];
+                    float dot = 0.f;
                     tmem_ld16(t_row, v);
 #pragma unroll 1
                     for (int u = 0; u < NU; ++u) {
                         float arg[16];
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 bb = *reinterpret_cast<const float4*>(vec + col0 + u * 16 + j);
-                            arg[j] = fmaf(__uint_as_float(v[j]), omega, bb.x);
-                            arg[j + 1] = fmaf(__uint_as_float(v[j + 1]), omega, bb.y);
-                            arg[j + 2] = fmaf(__uint_as_float(v[j + 2]), omega, bb.z);
-                            arg[j + 3] = fmaf(__uint_as_float(v[j + 3]), omega, bb.w);
+                        for (int j = 0; j < 4; ++j) {
+                            arg[4 * j] = omega * (__uint_as_float(v[4 * j]) + bn[j].x);
+                            arg[4 * j + 1] = omega * (__uint_as_float(v[4 * j + 1]) + bn[j].y);
+                            arg[4 * j + 2] = omega * (__uint_as_float(v[4 * j + 2]) + bn[j].z);
+                            arg[4 * j + 3] = omega * (__uint_as_float(v[4 * j + 3]) + bn[j].w);
                         }
-                        if (u + 1 < NU) tmem_ld16(t_row + (u + 1) * 16, v);      // in flight during the sincos below
+                        if (u + 1 < NU) {                        // in flight during the sincos below
+                            tmem_ld16(t_row + (u + 1) * 16, v);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc + (u + 1) * 16) + j);
+                        }
                         uint32_t so[8], co[8];
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi) {
@@ -352,41 +415,46 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) a8[j] = arg[gi * 8 + j];
                             if (mufu_hidden) sincos8<true>(a8, sn, cs); else sincos8<false>(a8, sn, cs);
+                            if (FWD && s == L) {                 // decode: u . sin(.) of this row, fp32
+                                const float* uv = g.dotvec + (size_t)fit * H + col0 + u * 16 + gi * 8;
+                                const float4 u0 = __ldg(reinterpret_cast<const float4*>(uv)), u1 = __ldg(reinterpret_cast<const float4*>(uv) + 1);
+                                dot = fmaf(u0.x, sn[0], dot); dot = fmaf(u0.y, sn[1], dot); dot = fmaf(u0.z, sn[2], dot); dot = fmaf(u0.w, sn[3], dot);
+                                dot = fmaf(u1.x, sn[4], dot); dot = fmaf(u1.y, sn[5], dot); dot = fmaf(u1.z, sn[6], dot); dot = fmaf(u1.w, sn[7], dot);
+                            }
 #pragma unroll
                             for (int j = 0; j < 8; j += 2) {
                                 so[(gi * 8 + j) / 2] = pack_bf16(sn[j], sn[j + 1]);
                                 co[(gi * 8 + j) / 2] = pack_bf16(cs[j], cs[j + 1]);
                             }
                         }
-                        act_store16(act_u32, r, col0 + u * 16, so);
-                        st_global_256_hint(cdst + u * 16, co, pol_keep);
+                        if (!(FWD && s == L)) {
+                            act_store16(act_u32, r, col0 + u * 16, so);
+                            if (!FWD) st_global_256_hint(cdst + u * 16, co, pol_keep);
+                        }
                     }
+                    if (FWD && s == L) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
                 } else if (s == L + 1) {
                     // ---------------- output layer: dY = 2 (y - t) / (N D), loss partial (siren.py:101)
-                    omap = &maps.yout; ochunks = D / 64;
-                    {
-                        const float* b = rec->params + g.b_off[L + 1];
-                        for (int j = st_tid; j < D; j += SET_THREADS) vec[j] = __ldg(b + j);
-                    }
-                    set_bar(bar_id, SET_THREADS);
                     const int ow = D / C::CG;                    // output columns of this thread
                     const int ocol0 = cg * ow;
+                    const float* bsrc = rec->params + g.b_off[L + 1] + ocol0;
                     const float* tn = rec->tnorm + (size_t)row * D + ocol0;
-                    uint32_t tt[16];
-                    ld_global_nc_na_256(tn, &tt[0]); ld_global_nc_na_256(tn + 8, &tt[8]);
+                    const int nuo = ow / 16;
+                    uint32_t ta[16], tb[16];                     // targets of this unit and the next: two units in flight
+                    ld_global_nc_na_256(tn, &ta[0]); ld_global_nc_na_256(tn + 8, &ta[8]);
+                    if (nuo > 1) { ld_global_nc_na_256(tn + 16, &tb[0]); ld_global_nc_na_256(tn + 24, &tb[8]); }
                     mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
                     tc_fence_after();
                     const uint32_t t_out = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + ocol0;
                     float sq = 0.f;
-                    uint32_t v[16];
-#pragma unroll 1
-                    for (int u = 0; u < ow / 16; ++u) {
+                    auto out_unit = [&](int u, uint32_t (&tt)[16]) {
+                        uint32_t v[16];
                         tmem_ld16(t_out + u * 16, v);
                         tmem_ld_wait();
                         uint32_t dout[8];
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 bb = *reinterpret_cast<const float4*>(vec + ocol0 + u * 16 + j);
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bsrc + u * 16 + j));
                             const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - __uint_as_float(tt[j + 0]);
                             const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - __uint_as_float(tt[j + 1]);
                             const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - __uint_as_float(tt[j + 2]);
@@ -395,8 +463,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             dout[j / 2] = pack_bf16(e0 * g.loss_scale, e1 * g.loss_scale);
                             dout[j / 2 + 1] = pack_bf16(e2 * g.loss_scale, e3 * g.loss_scale);
                         }
-                        if ((u + 1) * 16 < ow) { ld_global_nc_na_256(tn + (u + 1) * 16, &tt[0]); ld_global_nc_na_256(tn + (u + 1) * 16 + 8, &tt[8]); }
+                        if (u + 2 < nuo) { ld_global_nc_na_256(tn + (u + 2) * 16, &tt[0]); ld_global_nc_na_256(tn + (u + 2) * 16 + 8, &tt[8]); }
                         act_store16(act_u32, r, ocol0 + u * 16, dout);
+                    };
+#pragma unroll 1
+                    for (int u = 0; u < nuo; u += 2) {
+                        out_unit(u, ta);
+                        if (u + 1 < nuo) out_unit(u + 1, tb);
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -404,8 +477,6 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 } else {
                     // ---------------- backward: dz_{lp} = (dz_{lp+1} W_{lp+1}) * w cos_{lp}
                     const int lp = 2 * L + 2 - s;                // L, L-1, .., 0
-                    omap = &maps.zout[lp];
-                    set_bar(bar_id, SET_THREADS);
                     const __nv_bfloat16* csrc = scr + (size_t)lp * (BM * H);
                     uint32_t cc[PFD][8];
 #pragma unroll
@@ -431,21 +502,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         act_store16(act_u32, r, col0 + u * 16, dout);
                     }
                 }
-                // operand buffer complete: publish it to the tensor core (next MMA) and to global (dW operand)
+                // operand buffer complete: hand it to the MMA warp (stores it to global, then contracts it)
+                if (FWD && s == nsteps - 1) { tc_fence_before(); continue; }     // nothing consumes the last forward step
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
                 tc_fence_before();
-                set_bar(bar_id, SET_THREADS);
-                if (leader) {
-                    if (s < nsteps - 1) mbar_arrive(&act_ready[slot]);
-                    if (!(g.dbg & 1)) {
-                        for (int kc = 0; kc < ochunks; ++kc)
-                            tma_store_3d(omap, smem + slot * C::ACT_BYTES + kc * CHUNK_BYTES, kc * 64, mt * BM, fit);
-                        tma_store_commit();
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&act_ready[slot]);
             }
         }
-        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA retires
     }
 
     tc_fence_before();
@@ -479,29 +543,30 @@ inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __
 }
 
 template <int H>
-inline int launch_h(const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
+inline int launch_h(const ChainMaps& maps, const ChainArgs& a, bool fwd, cudaStream_t s) {
     const int tiles = a.nf * a.mtiles;
     const int grid = std::min(tiles, num_sms());
-    chain_kernel<H><<<grid, NTHREADS, Cfg<H>::SMEM, s>>>(maps, a);
+    if (fwd) chain_kernel<H, true><<<grid, NTHREADS, Cfg<H>::SMEM, s>>>(maps, a);
+    else chain_kernel<H, false><<<grid, NTHREADS, Cfg<H>::SMEM, s>>>(maps, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
 }
-inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
+inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, bool fwd, cudaStream_t s) {
     switch (H) {
-        case 64: return launch_h<64>(maps, a, s);
-        case 128: return launch_h<128>(maps, a, s);
-        case 256: return launch_h<256>(maps, a, s);
-        case 512: return launch_h<512>(maps, a, s);
+        case 64: return launch_h<64>(maps, a, fwd, s);
+        case 128: return launch_h<128>(maps, a, fwd, s);
+        case 256: return launch_h<256>(maps, a, fwd, s);
+        case 512: return launch_h<512>(maps, a, fwd, s);
         default: set_error("chain: unsupported H %d", H); return NA_ERR_UNSUPPORTED;
     }
 }
 
-// NERFATTN_SINCOS: 0 = polynomial everywhere, 1 = MUFU core in the hidden layers (default: their
-// results are rounded to bf16 at once), 3 = MUFU core in layer 0 too
+// NERFATTN_SINCOS: 0 = polynomial everywhere, 1 = MUFU core in the hidden layers only, 3 = in layer 0
+// too (default: every result is rounded to bf16 at once; the reduction is exact for |x| <= 8192)
 inline int sincos_mode() {
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("NERFATTN_SINCOS"); mode = e ? (int)strtol(e, nullptr, 0) & 3 : 1; }
+    if (mode < 0) { const char* e = getenv("NERFATTN_SINCOS"); mode = e ? (int)strtol(e, nullptr, 0) & 3 : 3; }
     return mode;
 }
 
@@ -521,7 +586,7 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
     a.loss_scale = 2.0f / ((float)N * (float)D);
     a.sincos_mode = sincos_mode();
     { const char* e = getenv("NERFATTN_CHAIN_DBG"); a.dbg = e ? atoi(e) : 0; }
-    if ((rc = launch(H, cm, a, s))) return rc;
+    if ((rc = launch(H, cm, a, false, s))) return rc;
     TcArgs base{};
     base.nb = nf; base.recs = recs;
     for (int l = L + 1; l >= 1; --l) {
@@ -537,15 +602,37 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
     return NA_OK;
 }
 
+// Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).
+inline int decode_parts(int H) { return (H <= 256) ? 2 : 4; }
+inline int build_fwd_maps(int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
+    int rc;
+    for (int l = 1; l <= L; ++l)
+        if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], H, H, nf, lm.P, false, H >= 256 ? 256 : H))) return rc;
+    return NA_OK;
+}
+inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
+                         const float* u, float* dotpart, cudaStream_t s) {
+    ChainArgs a{};
+    a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = N / BM; a.recs = recs;
+    for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
+    a.dotvec = u; a.dotpart = dotpart;
+    a.sincos_mode = sincos_mode();
+    return launch(H, cm, a, true, s);
+}
+
 inline int configure_all() {
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
         auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
-        acc(cudaFuncSetAttribute(chain_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<512>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<512>::SMEM));
+        acc(cudaFuncSetAttribute(chain_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<512>::SMEM));
     });
     if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(chain smem) failed: %s", cudaGetErrorString(err)); return NA_ERR_CUDA; }
     return NA_OK;

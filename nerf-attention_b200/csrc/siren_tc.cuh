@@ -502,22 +502,51 @@ inline void mirror_weights(const FitRec* recs, const LayerMap& lm, int nf, __nv_
 
 // gradient of layer 0 (fp32, positions never quantised): per 128-row tile
 //   xpart[f][t][j] = sum_r dz0[r][j] * x[r]      colpart0[f][t][j] = sum_r dz0[r][j]
+// HBM-bound (reads dz0 once): 16-byte loads, 8 columns per thread, the 128 rows of the tile split over
+// the thread groups of the block and combined through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 layer0_grad_kernel(const FitRec* recs, const __nv_bfloat16* dz0, size_t dz_fit, int N, int H, int mtiles,
                    float* xpart, float* colpart0) {
+    __shared__ float red[2][8][8 * 32 + 8];               // [sum kind][row slice][columns of this pass]
     const int f = blockIdx.y, t = blockIdx.x;
     const float* pos = recs[f].pos;
     const int r0 = t * 128, r1 = min(N, r0 + 128);
-    for (int j = threadIdx.x; j < H; j += blockDim.x) {
-        const __nv_bfloat16* src = dz0 + (size_t)f * dz_fit + j;
-        float sx = 0.f, s1 = 0.f;
-        for (int r = r0; r < r1; ++r) {
-            const float d = __bfloat162float(src[(size_t)r * H]);
-            sx = fmaf(d, __ldg(pos + r), sx);
-            s1 += d;
+    const int cu = threadIdx.x & 31, rs = threadIdx.x >> 5;          // column unit (8 columns), row slice
+    for (int c0 = 0; c0 < H; c0 += 256) {                             // 256 columns per pass
+        const int col = c0 + cu * 8;
+        float sx[8], s1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sx[k] = 0.f; s1[k] = 0.f; }
+        if (col < H) {
+            const __nv_bfloat16* src = dz0 + (size_t)f * dz_fit + col;
+#pragma unroll 4
+            for (int r = r0 + rs; r < r1; r += 8) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * H));
+                const float x = __ldg(pos + r);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a, b;
+                    unpack_bf16(w[k], a, b);
+                    sx[2 * k] = fmaf(a, x, sx[2 * k]); sx[2 * k + 1] = fmaf(b, x, sx[2 * k + 1]);
+                    s1[2 * k] += a; s1[2 * k + 1] += b;
+                }
+            }
         }
-        xpart[((size_t)f * mtiles + t) * H + j] = sx;
-        colpart0[((size_t)f * mtiles + t) * H + j] = s1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { red[0][rs][cu * 8 + k] = sx[k]; red[1][rs][cu * 8 + k] = s1[k]; }
+        __syncthreads();
+        {
+            const int j = threadIdx.x;                                // one column per thread
+            if (c0 + j < H) {
+                float ax = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) { ax += red[0][s][j]; a1 += red[1][s][j]; }
+                xpart[((size_t)f * mtiles + t) * H + c0 + j] = ax;
+                colpart0[((size_t)f * mtiles + t) * H + c0 + j] = a1;
+            }
+        }
+        __syncthreads();
     }
 }
 
