@@ -279,6 +279,38 @@ def run_native(args) -> None:
     dev_seconds = max_over_ranks(e0.elapsed_time(e1) / 1e3)
     results = batch.collect()
     launches = batch.launches_per_call() * args.steps
+
+    # ---- the dominant kernel alone, live: NERFATTN_PHASE makes the library launch only one class of
+    # kernels per epoch (1 = chain kernels, 2 = dW GEMMs + layer-0 gradient, 4 = Adam, 8 = none), so the
+    # difference to the "none" run is that class's device time per epoch (CUDA events, this stream).
+    phases = None
+    if args.precision == 'bf16' and os.environ.get('NERFATTN_NO_CHAIN', '0') in ('', '0'):
+        pe = max(20, min(100, args.epochs))
+        pbatch = batched.FitBatch(jobs, epochs=pe, device=str(dev), precision=args.precision, keep_initial=True)
+
+        def phase_ms(mask: int) -> float:
+            os.environ['NERFATTN_PHASE'] = str(mask)
+            try:
+                best = None
+                for _ in range(3):
+                    pbatch.reset()
+                    torch.cuda.synchronize()
+                    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    p0.record(); pbatch.launch(); p1.record()
+                    torch.cuda.synchronize()
+                    ms = p0.elapsed_time(p1)
+                    best = ms if best is None else min(best, ms)
+                return best
+            finally:
+                os.environ.pop('NERFATTN_PHASE', None)
+        base_ms = phase_ms(8)
+        phases = {'epochs': pe, 'fixed_ms': base_ms,
+                  'chain_ms_per_epoch': (phase_ms(1) - base_ms) / pe,
+                  'dw_l0grad_ms_per_epoch': (phase_ms(2) - base_ms) / pe,
+                  'adam_ms_per_epoch': (phase_ms(4) - base_ms) / pe,
+                  'all_ms_per_epoch': (phase_ms(7) - base_ms) / pe}
+        pbatch.collect()
+        del pbatch
     cos_keys = float(np.mean([r.final_cosine_mean for m, r in zip(meta, results) if m[2] == 0]))
     cos_vals = float(np.mean([r.final_cosine_mean for m, r in zip(meta, results) if m[2] == 1]))
     del batch
@@ -325,12 +357,35 @@ def run_native(args) -> None:
 
     peaks = measured_peaks()
     achieved = total_flops * args.steps / dev_seconds / 1e12            # per GPU: max-over-ranks time, own flops
-    if args.precision == 'bf16':
+    traffic = None
+    tpath = ROOT / 'profiles' / 'ncu_traffic.json'
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text())
+    if args.precision == 'bf16' and phases:
+        # chain kernel = forward + dX of every fit: 4N(LH^2+HD) + 2NH FLOPs per fit-epoch (dW is the rest of F)
+        chain_flops = sum(4 * args.seq_len * (j.config.hidden_layers * j.config.hidden_features ** 2 +
+                                              j.config.hidden_features * HEAD_DIM) +
+                          2 * args.seq_len * j.config.hidden_features for j in jobs)
+        k_ach = chain_flops / (phases['chain_ms_per_epoch'] * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': k_ach, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+                'frac': k_ach / peaks['bf16_sustained'],
+                'traffic': (traffic or {}).get('chain_dram_bytes_per_epoch'),
+                'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a seconds-long step)",
+                'kernel': 'chain::chain_kernel<H,NS,false> (fused forward + loss + dX per 128-row tile; one launch per '
+                          'shape group and epoch, 5 per epoch): algorithmic FLOPs 4N(LH^2+HD)+2NH per fit-epoch, all 280 '
+                          'fits / summed device time of the 5 launches of one epoch (NERFATTN_PHASE=1 minus =8, CUDA events)',
+                'per_launch': 'one epoch = 5 chain launches; achieved/traffic are per epoch (sum over the 5)',
+                'share_of_step': phases['chain_ms_per_epoch'] / phases['all_ms_per_epoch'],
+                'phases_ms_per_epoch': phases,
+                'whole_step': {'achieved': achieved, 'frac': achieved / peaks['bf16_sustained'],
+                               'note': 'all kernels (chain + dW + layer-0 gradient + Adam): F = 6N(LH^2+HD)+4NH per '
+                                       'fit-epoch / step time',
+                               'traffic': (traffic or {}).get('step_dram_bytes_per_epoch')}}
+    elif args.precision == 'bf16':
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / peaks['bf16_sustained'], 'traffic': None,
                 'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a seconds-long step)",
-                'kernel': 'whole step (tc_gemm_kernel fwd/out/dX/dW + SIMT layer0/Adam): algorithmic GEMM FLOPs '
-                          '6N(LH^2+HD)+4NH per fit-epoch / step time'}
+                'kernel': 'whole step (unfused tc_gemm_kernel path, NERFATTN_NO_CHAIN=1)'}
     else:
         fp32_peak = 148 * 128 * 2 * (clocks['sm_mhz'] or 1965.0) * 1e6 / 1e12
         roof = {'bound': 'fp32-fma', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',

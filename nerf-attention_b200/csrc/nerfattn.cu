@@ -525,7 +525,7 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
                                 g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
                                 g.losspart_per_fit, g.mtiles, s);
                 if (r2) return r2;
-                launch_adam(g, plan, beta1, beta2, eps, s);
+                if (!g.use_chain || (chain::phase_mask() & 4)) launch_adam(g, plan, beta1, beta2, eps, s);
             }
             if (parallel) { cudaEventRecord(joins[gi], s); cudaStreamWaitEvent(main, joins[gi], 0); }
         }

@@ -40,12 +40,14 @@ constexpr int NEPI = 16;                          // epilogue warps 4..19
 constexpr int NTHREADS = (NCTRL + NEPI) * 32;     // 640
 constexpr int CHUNK_BYTES = BM * 64 * 2;          // one K-chunk of an A operand: 128 rows x 64 bf16
 constexpr int STAGE_BYTES = 256 * 64 * 2;         // one K-chunk of a weight operand: <= 256 x 64 bf16
-constexpr int STAGES = 3;
+constexpr int SMEM_BUDGET = 227 * 1024 - 512;     // dynamic shared memory per CTA, minus the barrier block
 
-template <int H> struct Cfg {
+// NS = tiles in flight per CTA (2 needs 2 x max(H, 256) accumulator columns and operand buffers)
+template <int H, int NS> struct Cfg {
+    static_assert(NS == 1 || (NS == 2 && H <= 256), "two slots need H <= 256");
     static constexpr int BN = (H >= 256) ? 256 : H;              // N of one hidden-layer MMA
     static constexpr int NPARTS = H / BN;
-    static constexpr int NSLOT = (H <= 256) ? 2 : 1;
+    static constexpr int NSLOT = NS;
     static constexpr int EPW = NEPI / NSLOT;                      // epilogue warps per slot
     static constexpr int CG = EPW / 4;                            // column groups per slot
     static constexpr int CW = H / CG;                             // columns per thread in a hidden step
@@ -53,7 +55,9 @@ template <int H> struct Cfg {
     static constexpr int ACT_CHUNKS = ((H > 256) ? H : 256) / 64;   // dY (D <= 256) aliases the buffer
     static constexpr int ACT_BYTES = ACT_CHUNKS * CHUNK_BYTES;
     static constexpr int ACC_COLS = (H > 256) ? 512 : 256;
+    static constexpr int STAGES = ((SMEM_BUDGET - NSLOT * ACT_BYTES) / STAGE_BYTES < 6) ? (SMEM_BUDGET - NSLOT * ACT_BYTES) / STAGE_BYTES : 6;
     static constexpr int SMEM = NSLOT * ACT_BYTES + STAGES * STAGE_BYTES + 256;
+    static_assert(STAGES >= 3, "weight ring");
     static_assert(NU >= 1 && CW % 16 == 0, "column split");
 };
 
@@ -77,7 +81,8 @@ struct ChainMaps {
 inline bool shape_supported(int N, int D, int H, int L) {
     return tc::shape_supported(N, D, H, L) && L >= 1;
 }
-inline int loss_partials_per_fit(int N, int H) { return (N / BM) * (H <= 256 ? NEPI / 2 : NEPI); }   // one per epilogue warp of the tile
+inline int slots_for(int H);
+inline int loss_partials_per_fit(int N, int H) { return (N / BM) * (NEPI / slots_for(H)); }   // one per epilogue warp of the tile
 
 __device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -138,7 +143,7 @@ __device__ __forceinline__ void act_store16(uint32_t act_u32, int r, int col, co
 struct Step { int layer; int mn; int kch; int n; int nparts; };
 template <int H>
 __device__ __forceinline__ Step step_info(int s, int L, int D) {
-    using C = Cfg<H>;
+    using C = Cfg<H, 1>;
     Step st;
     if (s <= L) { st.layer = s; st.mn = 0; st.kch = H / 64; st.n = C::BN; st.nparts = C::NPARTS; }
     else if (s == L + 1) { st.layer = L + 1; st.mn = 0; st.kch = H / 64; st.n = D; st.nparts = 1; }
@@ -156,11 +161,12 @@ __device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], floa
 // (evaluate.py:173-242 times this reconstruction): E0, S_1..S_L, and instead of materialising K the
 // last sine epilogue reduces u . sin(.) per position, u = Wf^T (q * std) (decode.cuh) -- no cos, no
 // global stores except one partial score per position and column group.
-template <int H, bool FWD>
+template <int H, int NS, bool FWD>
 __global__ void __launch_bounds__(NTHREADS, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
-    using C = Cfg<H>;
+    using C = Cfg<H, NS>;
     constexpr int NSLOT = C::NSLOT;
+    constexpr int STAGES = C::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_ring = smem + NSLOT * C::ACT_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + STAGES * STAGE_BYTES);
@@ -520,9 +526,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 }
 
 // ------------------------------------------------------------------ host
+// NERFATTN_CHAIN_SLOTS=1 forces one tile in flight per CTA (16 epilogue warps on it, deeper weight ring)
+inline int slots_for(int H) {
+    const char* e = getenv("NERFATTN_CHAIN_SLOTS");
+    return (H <= 256 && !(e && atoi(e) == 1)) ? 2 : 1;
+}
 inline size_t scratch_elems(int H, int L) {
-    const int nslot = (H <= 256) ? 2 : 1;
-    return (size_t)num_sms() * nslot * (L + 1) * BM * H;
+    return (size_t)num_sms() * 2 * (L + 1) * BM * H;
 }
 
 inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16,
@@ -546,8 +556,18 @@ template <int H>
 inline int launch_h(const ChainMaps& maps, const ChainArgs& a, bool fwd, cudaStream_t s) {
     const int tiles = a.nf * a.mtiles;
     const int grid = std::min(tiles, num_sms());
-    if (fwd) chain_kernel<H, true><<<grid, NTHREADS, Cfg<H>::SMEM, s>>>(maps, a);
-    else chain_kernel<H, false><<<grid, NTHREADS, Cfg<H>::SMEM, s>>>(maps, a);
+    if constexpr (H <= 256) {
+        if (slots_for(H) == 2) {
+            if (fwd) chain_kernel<H, 2, true><<<grid, NTHREADS, Cfg<H, 2>::SMEM, s>>>(maps, a);
+            else chain_kernel<H, 2, false><<<grid, NTHREADS, Cfg<H, 2>::SMEM, s>>>(maps, a);
+        } else {
+            if (fwd) chain_kernel<H, 1, true><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
+            else chain_kernel<H, 1, false><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
+        }
+    } else {
+        if (fwd) chain_kernel<H, 1, true><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
+        else chain_kernel<H, 1, false><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
@@ -565,9 +585,16 @@ inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, bool fwd, cu
 // NERFATTN_SINCOS: 0 = polynomial everywhere, 1 = MUFU core in the hidden layers only, 3 = in layer 0
 // too (default: every result is rounded to bf16 at once; the reduction is exact for |x| <= 8192)
 inline int sincos_mode() {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("NERFATTN_SINCOS"); mode = e ? (int)strtol(e, nullptr, 0) & 3 : 3; }
-    return mode;
+    const char* e = getenv("NERFATTN_SINCOS");
+    return e ? (int)strtol(e, nullptr, 0) & 3 : 3;
+}
+// NERFATTN_PHASE (profiling only; results are meaningless): 1 = launch only the chain kernels of an
+// epoch, 2 = only the dW GEMMs + layer-0 gradient, 4 = only Adam; 0 / unset = everything.  bench.py
+// uses it to time the dominant kernel alone, live, with CUDA events.
+inline int phase_mask() {
+    const char* e = getenv("NERFATTN_PHASE");
+    const int m = e ? atoi(e) : 0;
+    return m ? m : 7;
 }
 
 // One training epoch of one group: the chain, then the dW GEMMs (contraction over all rows of a fit)
@@ -586,7 +613,9 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
     a.loss_scale = 2.0f / ((float)N * (float)D);
     a.sincos_mode = sincos_mode();
     { const char* e = getenv("NERFATTN_CHAIN_DBG"); a.dbg = e ? atoi(e) : 0; }
-    if ((rc = launch(H, cm, a, false, s))) return rc;
+    const int phases = phase_mask();
+    if ((phases & 1) && (rc = launch(H, cm, a, false, s))) return rc;
+    if (!(phases & 2)) return NA_OK;
     TcArgs base{};
     base.nb = nf; base.recs = recs;
     for (int l = L + 1; l >= 1; --l) {
@@ -603,7 +632,7 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
 }
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).
-inline int decode_parts(int H) { return (H <= 256) ? 2 : 4; }
+inline int decode_parts(int H) { return slots_for(H) == 2 ? 2 : 4; }
 inline int build_fwd_maps(int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
     int rc;
     for (int l = 1; l <= L; ++l)
@@ -625,14 +654,12 @@ inline int configure_all() {
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
         auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
-        acc(cudaFuncSetAttribute(chain_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<512>::SMEM));
-        acc(cudaFuncSetAttribute(chain_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<512>::SMEM));
+#define NA_CHAIN_CFG(HH, NS) \
+        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM)); \
+        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM));
+        NA_CHAIN_CFG(64, 2) NA_CHAIN_CFG(128, 2) NA_CHAIN_CFG(256, 2)
+        NA_CHAIN_CFG(64, 1) NA_CHAIN_CFG(128, 1) NA_CHAIN_CFG(256, 1) NA_CHAIN_CFG(512, 1)
+#undef NA_CHAIN_CFG
     });
     if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(chain smem) failed: %s", cudaGetErrorString(err)); return NA_ERR_CUDA; }
     return NA_OK;
