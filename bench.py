@@ -284,7 +284,7 @@ def run_native(args) -> None:
     # kernels per epoch (1 = chain kernels, 2 = dW GEMMs + layer-0 gradient, 4 = Adam, 8 = none), so the
     # difference to the "none" run is that class's device time per epoch (CUDA events, this stream).
     phases = None
-    if args.precision == 'bf16' and os.environ.get('NERFATTN_NO_CHAIN', '0') in ('', '0'):
+    if rank == 0 and args.precision == 'bf16' and os.environ.get('NERFATTN_NO_CHAIN', '0') in ('', '0'):
         pe = max(20, min(100, args.epochs))
         pbatch = batched.FitBatch(jobs, epochs=pe, device=str(dev), precision=args.precision, keep_initial=True)
 
