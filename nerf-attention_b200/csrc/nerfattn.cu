@@ -247,7 +247,8 @@ static void fp32_output_layer(const Group& g, const float* actL, bool eval, cuda
     }
 }
 
-static void launch_adam(const Group& g, const Plan& plan, double beta1, double beta2, double eps, cudaStream_t s) {
+static void launch_adam(const Group& g, const Plan& plan, double beta1, double beta2, double eps, cudaStream_t s,
+                        bool layer0_only = false) {
     f32::AdamArgs a{};
     a.recs = g.d_recs; a.lm = g.lm;
     a.et.epoch = plan.d_epoch; a.et.step_size = plan.d_step_size; a.et.bc2_sqrt = plan.d_bc2;
@@ -263,8 +264,9 @@ static void launch_adam(const Group& g, const Plan& plan, double beta1, double b
     // 64-thread blocks (3 K registers, no shared memory): small enough to be co-scheduled on SMs whose
     // registers and shared memory are almost entirely held by another group's chain CTA, so this
     // HBM-bound update overlaps that group's issue-bound kernel instead of waiting for free SMs
+    a.p_end = layer0_only ? g.lm.w_off[1] : g.lm.P;
     const int adam_threads = env_flag("NERFATTN_ADAM256") ? 256 : 64;
-    dim3 grid(ceil_div(g.lm.P, adam_threads * 4), g.nf);
+    dim3 grid(ceil_div(a.p_end, adam_threads * 4), g.nf);
     f32::adam_kernel<<<grid, adam_threads, 0, s>>>(a);
 }
 
@@ -517,15 +519,21 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
             const Group& g = plan.groups[gi];
             if (precision == NA_PREC_FP32) fp32_epoch(g, plan, beta1, beta2, eps, s);
             else {
+                chain::AdamFuse af{};
+                const bool fused = g.use_chain && chain::adam_fused();
+                if (fused) {
+                    af.epoch = plan.d_epoch; af.step_size = plan.d_step_size; af.bc2 = plan.d_bc2;
+                    af.beta1 = (float)beta1; af.beta2 = (float)beta2; af.eps = (float)eps; af.wbf16 = g.wbf16;
+                }
                 int r2 = g.use_chain
                     ? chain::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, *g.cmaps, g.act, g.cosb, g.dy,
                                    g.chain_scratch, g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                   g.losspart_per_fit, g.mtiles, s)
+                                   g.losspart_per_fit, g.mtiles, af, s)
                     : tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
                                 g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
                                 g.losspart_per_fit, g.mtiles, s);
                 if (r2) return r2;
-                if (!g.use_chain || (chain::phase_mask() & 4)) launch_adam(g, plan, beta1, beta2, eps, s);
+                if (!g.use_chain || (chain::phase_mask() & 4)) launch_adam(g, plan, beta1, beta2, eps, s, fused);
             }
             if (parallel) { cudaEventRecord(joins[gi], s); cudaStreamWaitEvent(main, joins[gi], 0); }
         }
@@ -730,7 +738,7 @@ extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void*
         // fused forward chain: layer 0, the hidden layers and the u . sin(.) reduction in one kernel
         if ((rc = chain::configure_all())) return rc;
         chain::ChainMaps cm;
-        if ((rc = chain::build_fwd_maps(g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
+        if ((rc = chain::build_fwd_maps(g.N, g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
         if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, p.u, p.dotpart, stream))) return rc;
     } else {
         const int bn = tc::hidden_bn(g.H);

@@ -40,6 +40,7 @@ constexpr int NEPI = 16;                          // epilogue warps 4..19
 constexpr int NTHREADS = (NCTRL + NEPI) * 32;     // 640
 constexpr int CHUNK_BYTES = BM * 64 * 2;          // one K-chunk of an A operand: 128 rows x 64 bf16
 constexpr int STAGE_BYTES = 256 * 64 * 2;         // one K-chunk of a weight operand: <= 256 x 64 bf16
+constexpr bool kClusterDefault = false;           // tuned on B200, see profiles/README.md
 constexpr int SMEM_BUDGET = 227 * 1024 - 512;     // dynamic shared memory per CTA, minus the barrier block
 
 // NS = tiles in flight per CTA (2 needs 2 x max(H, 256) accumulator columns and operand buffers)
@@ -115,9 +116,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 2-CTA cluster: one L2 read feeds the same ring stage of both CTAs (they work on adjacent row tiles of
+// the same fit, i.e. the same weights), and a stage is released to the loaders by both MMA warps.
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
@@ -161,12 +187,19 @@ __device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], floa
 // (evaluate.py:173-242 times this reconstruction): E0, S_1..S_L, and instead of materialising K the
 // last sine epilogue reduces u . sin(.) per position, u = Wf^T (q * std) (decode.cuh) -- no cos, no
 // global stores except one partial score per position and column group.
-template <int H, int NS, bool FWD>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the pair (2c, 2c+1) takes adjacent row tiles of one fit, each
+// CTA issues half of every weight stage's 64 x 64 boxes as a multicast to both, so the L2 -> SM weight
+// traffic and the time to fill a stage halve; nothing else is shared (each CTA issues its own MMAs).
+template <int H, int NS, bool FWD, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     using C = Cfg<H, NS>;
     constexpr int NSLOT = C::NSLOT;
     constexpr int STAGES = C::STAGES;
+    const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
+    // tile of (round, slot): clusters stride over tile pairs, CTAs of a cluster take consecutive tiles
+    const int cl_stride = (int)gridDim.x / CL;
+    auto tile_of = [&](int round, int slot) { return CL * ((int)blockIdx.x / CL + (round * NSLOT + slot) * cl_stride) + (int)crank; };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_ring = smem + NSLOT * C::ACT_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + STAGES * STAGE_BYTES);
@@ -183,7 +216,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) { printf("nerfattn: chain smem base not 1024-aligned\n"); __trap(); }
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], C::EPW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -193,13 +226,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();              // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     // register reallocation (sm_90+): the two control warps need few registers, the epilogue warps want more
     // than the 96 a 640-thread CTA gets by default
     if (warp < NCTRL) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ===================================================== TMA producer: weights only
         // The ring holds 96 KB, one hidden step reads 128 KB, and the 16 CTAs working on a fit ask for
@@ -211,7 +245,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 const CUtensorMap* map = st.mn ? &maps.wmn[st.layer] : &maps.wk[st.layer];
                 for (int np = 0; np < st.nparts; ++np)
                     for (int kc = 0; kc < st.kch; ++kc) {
-                        if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256, fit);
+                        if (CL == 2) {
+                            for (int i = (int)crank; i < st.n / 64; i += 2) {
+                                if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256 + i * 64, fit);
+                                else tma_prefetch_3d(map, np * 256 + i * 64, kc * 64, fit);
+                            }
+                        } else if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256, fit);
                         else
                             for (int i = 0; i < st.n / 64; ++i) tma_prefetch_3d(map, np * 256 + i * 64, kc * 64, fit);
                     }
@@ -225,23 +264,22 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 l2_prefetch_bulk(g.recs[fit].tnorm + (size_t)mt * BM * D, (uint32_t)(BM * D * 4));
             };
             for (int slot = 0; slot < NSLOT; ++slot) {
-                const int tile = blockIdx.x + slot * gridDim.x;
+                const int tile = tile_of(0, slot);
                 if (tile < total_tiles) { prefetch_step(1, tile / g.mtiles); prefetch_targets(tile); }
             }
             for (int round = 0;; ++round) {
-                const int t0 = blockIdx.x + round * NSLOT * gridDim.x;
-                if (t0 >= total_tiles) break;
+                if (tile_of(round, 0) >= total_tiles) break;
                 for (int s = 1; s < nsteps; ++s) {
                     const Step st = step_info<H>(s, L, D);
                     const CUtensorMap* map = st.mn ? &maps.wmn[st.layer] : &maps.wk[st.layer];
                     const uint32_t tx = (uint32_t)st.n * 128u;
                     for (int slot = 0; slot < NSLOT; ++slot) {
-                        const int tile = t0 + slot * gridDim.x;
+                        const int tile = tile_of(round, slot);
                         if (tile >= total_tiles) break;
                         const int fit = tile / g.mtiles;
                         if (s + 1 < nsteps) prefetch_step(s + 1, fit);
                         else {
-                            const int ntile = tile + NSLOT * gridDim.x;
+                            const int ntile = tile_of(round + 1, slot);
                             if (ntile < total_tiles) {
                                 if (ntile / g.mtiles != fit) prefetch_step(1, ntile / g.mtiles);
                                 prefetch_targets(ntile);
@@ -252,7 +290,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                                 mbar_wait(&empty[stage], phase ^ 1);
                                 mbar_expect_tx(&full[stage], tx);
                                 uint8_t* sb = smem_ring + stage * STAGE_BYTES;
-                                if (!st.mn) tma_load_3d(sb, map, &full[stage], kc * 64, np * 256, fit);
+                                if (CL == 2) {
+                                    // 64 x 64 boxes (the same map serves K-major and MN-major use); this CTA issues every other one
+                                    for (int i = (int)crank; i < st.n / 64; i += 2) {
+                                        if (!st.mn) tma_load_3d_mc(sb + i * 8192, map, &full[stage], kc * 64, np * 256 + i * 64, fit, 3);
+                                        else tma_load_3d_mc(sb + i * 8192, map, &full[stage], np * 256 + i * 64, kc * 64, fit, 3);
+                                    }
+                                } else if (!st.mn) tma_load_3d(sb, map, &full[stage], kc * 64, np * 256, fit);
                                 else
                                     for (int i = 0; i < st.n / 64; ++i)
                                         tma_load_3d(sb + i * 8192, map, &full[stage], np * 256 + i * 64, kc * 64, fit);
@@ -269,9 +313,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         // (dz_0) and hands the buffer back.  acc_full[slot] = accumulator complete AND buffer free.
         int stage = 0; uint32_t phase = 0;
         uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot]
+        const uint64_t pol_stream = policy_evict_first();   // h_l / dz_l / dY are read by a later kernel: do not displace the cos scratch
         for (int round = 0;; ++round) {
-            const int t0 = blockIdx.x + round * NSLOT * gridDim.x;
-            if (t0 >= total_tiles) break;
+            if (tile_of(round, 0) >= total_tiles) break;
             for (int s = 1; s <= (FWD ? nsteps - 1 : nsteps); ++s) {
                 const Step st = step_info<H>(s < nsteps ? s : 1, L, D);
                 const uint32_t idesc = make_idesc(st.n, false, st.mn != 0);
@@ -282,7 +326,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 const CUtensorMap* omap = (ps <= L) ? &maps.hout[ps] : (ps == L + 1) ? &maps.yout : &maps.zout[2 * L + 2 - ps];
                 const int ochunks = (ps == L + 1) ? D / 64 : H / 64;
                 for (int slot = 0; slot < NSLOT; ++slot) {
-                    const int tile = t0 + slot * (int)gridDim.x;
+                    const int tile = tile_of(round, slot);
                     if (tile >= total_tiles) break;
                     const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
                     mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
@@ -290,7 +334,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     tc_fence_after();
                     uint8_t* const act = smem + slot * C::ACT_BYTES;
                     if (!FWD && lane == 0 && !(g.dbg & 1)) {
-                        for (int kc = 0; kc < ochunks; ++kc) tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, mt * BM, fit);
+                        for (int kc = 0; kc < ochunks; ++kc) tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, mt * BM, fit, pol_stream);
                         tma_store_commit();
                     }
                     if (s == nsteps) {
@@ -311,7 +355,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                                 for (int k = 0; k < 64 / UMMA_K; ++k)
                                     tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
                                                 (kc > 0 || k > 0) ? 1u : 0u);
-                                tc_commit(&empty[stage]);
+                                if (CL == 2) tc_commit_mc(&empty[stage], 3); else tc_commit(&empty[stage]);
                                 if (np == st.nparts - 1 && kc == st.kch - 1) {
                                     if (!FWD) tma_store_wait_read();  // the store has read the buffer long before the MMAs retire
                                     tc_commit(&acc_full[slot]);
@@ -345,7 +389,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H) + (size_t)r * H + col0;
         uint32_t acc_phase = 0;
         for (int round = 0;; ++round) {
-            const int tile = blockIdx.x + (round * NSLOT + slot) * gridDim.x;
+            const int tile = tile_of(round, slot);
             if (tile >= total_tiles) break;
             const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
             const FitRec* rec = &g.recs[fit];
@@ -520,6 +564,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();              // the peer may still multicast into / arrive on this CTA's shared memory
     tc_fence_after();
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -530,6 +575,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 inline int slots_for(int H) {
     const char* e = getenv("NERFATTN_CHAIN_SLOTS");
     return (H <= 256 && !(e && atoi(e) == 1)) ? 2 : 1;
+}
+// NERFATTN_CLUSTER=0 disables the 2-CTA cluster (multicast weight loads); it needs an even number of row tiles
+// per fit so that a pair never straddles two fits
+inline bool use_cluster(int N) {
+    const char* e = getenv("NERFATTN_CLUSTER");
+    const bool on = e ? atoi(e) != 0 : kClusterDefault;
+    const char* sl = getenv("NERFATTN_CHAIN_SLOTS");
+    return on && !(sl && atoi(sl) == 1) && (N / BM) % 2 == 0 && num_sms() % 2 == 0;
 }
 inline size_t scratch_elems(int H, int L) {
     return (size_t)num_sms() * 2 * (L + 1) * BM * H;
@@ -545,30 +598,40 @@ inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __
     if ((rc = make_operand_map(&m.yout, dy, N, D, nf, (size_t)N * D, false, BM))) return rc;
     for (int l = 1; l <= L + 1; ++l) {
         const int rows = lm.out_dim[l];
-        const int box = (l == L + 1) ? D : (H >= 256 ? 256 : H);
+        const int box = use_cluster(N) ? 64 : (l == L + 1) ? D : (H >= 256 ? 256 : H);
         if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], rows, H, nf, lm.P, false, box))) return rc;
         if ((rc = make_operand_map(&m.wmn[l], wbf16 + lm.w_off[l], rows, H, nf, lm.P, true, 0))) return rc;
     }
     return NA_OK;
 }
 
+template <int H, int NS, bool FWD, int CL>
+inline cudaError_t launch_one(int grid, const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = Cfg<H, NS>::SMEM; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, chain_kernel<H, NS, FWD, CL>, maps, a);
+}
 template <int H>
 inline int launch_h(const ChainMaps& maps, const ChainArgs& a, bool fwd, cudaStream_t s) {
     const int tiles = a.nf * a.mtiles;
-    const int grid = std::min(tiles, num_sms());
-    if constexpr (H <= 256) {
-        if (slots_for(H) == 2) {
-            if (fwd) chain_kernel<H, 2, true><<<grid, NTHREADS, Cfg<H, 2>::SMEM, s>>>(maps, a);
-            else chain_kernel<H, 2, false><<<grid, NTHREADS, Cfg<H, 2>::SMEM, s>>>(maps, a);
-        } else {
-            if (fwd) chain_kernel<H, 1, true><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
-            else chain_kernel<H, 1, false><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
-        }
+    const bool cl = use_cluster(a.N);
+    int grid = std::min(tiles, num_sms());
+    if (cl) grid &= ~1;
+    cudaError_t e;
+    constexpr int NSD = (H <= 256) ? 2 : 1;                  // default slots
+    if (cl && slots_for(H) == NSD) {
+        e = fwd ? launch_one<H, NSD, true, 2>(grid, maps, a, s) : launch_one<H, NSD, false, 2>(grid, maps, a, s);
+    } else if constexpr (H <= 256) {
+        if (slots_for(H) == 2) e = fwd ? launch_one<H, 2, true, 1>(grid, maps, a, s) : launch_one<H, 2, false, 1>(grid, maps, a, s);
+        else e = fwd ? launch_one<H, 1, true, 1>(grid, maps, a, s) : launch_one<H, 1, false, 1>(grid, maps, a, s);
     } else {
-        if (fwd) chain_kernel<H, 1, true><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
-        else chain_kernel<H, 1, false><<<grid, NTHREADS, Cfg<H, 1>::SMEM, s>>>(maps, a);
+        e = fwd ? launch_one<H, 1, true, 1>(grid, maps, a, s) : launch_one<H, 1, false, 1>(grid, maps, a, s);
     }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
 }
@@ -599,10 +662,18 @@ inline int phase_mask() {
 
 // One training epoch of one group: the chain, then the dW GEMMs (contraction over all rows of a fit)
 // and the layer-0 gradient; Adam follows in the caller.
+struct AdamFuse {            // non-null epoch => the dW epilogues apply Adam to layers 1..L+1 (siren_tc.cuh)
+    const int* epoch; const float* step_size; const float* bc2; float beta1, beta2, eps;
+    __nv_bfloat16* wbf16;
+};
+// measured on B200: 2.01 ms per epoch fused vs 1.92 ms with the separate coalesced adam_kernel (the dW epilogue owns one
+// row per thread, so its p/m/v accesses are 32 B per lane at row stride) -- off by default
+inline bool adam_fused() { const char* e = getenv("NERFATTN_ADAM_FUSED"); return e ? atoi(e) != 0 : false; }
+
 inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const GroupMaps& m,
                  const ChainMaps& cm, void* const* act, void* const* dzs, void* dy, __nv_bfloat16* scratch,
                  float* gradpart, float* colpart, const size_t* colpart_layer_off, float* xpart, float* losspart,
-                 int losspart_per_fit, int mtiles, cudaStream_t s) {
+                 int losspart_per_fit, int mtiles, const AdamFuse& af, cudaStream_t s) {
     int rc;
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
@@ -624,6 +695,12 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
         w.M = width; w.N = H; w.K = N;
         w.fout = gradpart; w.fout_fit = lm.P; w.fout_off = lm.w_off[l]; w.ldf = H;
         w.biasgrad = colpart + colpart_layer_off[l]; w.biasgrad_fit = width;
+        if (af.epoch && (phases & 4)) {
+            w.adam_epoch = af.epoch; w.adam_step_size = af.step_size; w.adam_bc2 = af.bc2;
+            w.adam_beta1 = af.beta1; w.adam_beta2 = af.beta2; w.adam_eps = af.eps;
+            w.adam_w_off = lm.w_off[l]; w.adam_b_off = lm.b_off[l];
+            w.adam_wbf16 = af.wbf16; w.adam_wbf16_fit = lm.P;
+        }
         if ((rc = launch_bn<kDw, true, true>(dw_bn(H), m.dw[l], w, s))) return rc;
     }
     layer0_grad_kernel<<<dim3(mtiles, nf), 256, 0, s>>>(recs, (const __nv_bfloat16*)dzs[0], (size_t)N * H, N, H, mtiles,
@@ -633,10 +710,11 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).
 inline int decode_parts(int H) { return slots_for(H) == 2 ? 2 : 4; }
-inline int build_fwd_maps(int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
+inline int build_fwd_maps(int N, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
     int rc;
     for (int l = 1; l <= L; ++l)
-        if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], H, H, nf, lm.P, false, H >= 256 ? 256 : H))) return rc;
+        if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], H, H, nf, lm.P, false,
+                                   use_cluster(N) ? 64 : H >= 256 ? 256 : H))) return rc;
     return NA_OK;
 }
 inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
@@ -654,11 +732,12 @@ inline int configure_all() {
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
         auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
-#define NA_CHAIN_CFG(HH, NS) \
-        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM)); \
-        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM));
-        NA_CHAIN_CFG(64, 2) NA_CHAIN_CFG(128, 2) NA_CHAIN_CFG(256, 2)
-        NA_CHAIN_CFG(64, 1) NA_CHAIN_CFG(128, 1) NA_CHAIN_CFG(256, 1) NA_CHAIN_CFG(512, 1)
+#define NA_CHAIN_CFG(HH, NS, CL) \
+        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM)); \
+        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, true, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM));
+        NA_CHAIN_CFG(64, 2, 1) NA_CHAIN_CFG(128, 2, 1) NA_CHAIN_CFG(256, 2, 1)
+        NA_CHAIN_CFG(64, 1, 1) NA_CHAIN_CFG(128, 1, 1) NA_CHAIN_CFG(256, 1, 1) NA_CHAIN_CFG(512, 1, 1)
+        NA_CHAIN_CFG(64, 2, 2) NA_CHAIN_CFG(128, 2, 2) NA_CHAIN_CFG(256, 2, 2) NA_CHAIN_CFG(512, 1, 2)
 #undef NA_CHAIN_CFG
     });
     if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(chain smem) failed: %s", cudaGetErrorString(err)); return NA_ERR_CUDA; }

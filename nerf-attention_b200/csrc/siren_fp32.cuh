@@ -401,6 +401,7 @@ struct AdamArgs {
     float beta1, beta2, eps;
     // BF16 copies of the hidden/output weights for the tensor path (nullptr in fp32 mode)
     __nv_bfloat16* wbf16; size_t wbf16_fit;
+    int p_end;              // parameters [0, p_end) are updated here (the rest in the dW epilogues when fused)
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
         for (int i = 0; i < a.losspart_per_fit; ++i) s += a.losspart[(size_t)f * a.losspart_per_fit + i];
         rec.losses[e] = s * a.loss_inv_count;
     }
-    if (p >= a.lm.P) return;
+    if (p >= a.p_end) return;
 
     // which layer / weight-or-bias does p belong to
     int layer = 0;
