@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NERFATTN_ABI_VERSION 5
+#define NERFATTN_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define NA_API __attribute__((visibility("default")))
@@ -117,6 +117,19 @@ NA_API int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t epo
                          const double* lr_table, double beta1, double beta2, double eps,
                          int32_t first_step, int32_t precision,
                          void* workspace, size_t workspace_bytes, na_stream_t stream);
+
+/*
+ * Same, plus the reference's progress metrics (nerf_attention/siren.py:107-115): whenever
+ * (epoch + 1) % log_every == 0 the de-normalised MSE and the mean CosSim of the prediction made
+ * with the weights that epoch starts from are written to
+ *   progress[((epoch + 1) / log_every - 1) * nfits * 2 + fit * 2 + {0: RealMSE, 1: CosSim}]
+ * (DEVICE float array of (epochs / log_every) * nfits * 2 values; fp32 evaluation in every mode).
+ * log_every <= 0 or progress == NULL: no progress metrics (== nerfattn_fit_batched).
+ */
+NA_API int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int32_t epochs,
+                            const double* lr_table, double beta1, double beta2, double eps,
+                            int32_t first_step, int32_t precision, int32_t log_every, float* progress,
+                            void* workspace, size_t workspace_bytes, na_stream_t stream);
 
 /* Number of kernel launches nerfattn_fit_batched enqueues for this job list (graph replays
  * counted once per epoch): set-up + epochs * per-epoch + final metrics. */

@@ -37,6 +37,7 @@ struct FitRec {
     float* std_out;         // caller's [D]
     float omega;
     int uniq;               // index of the unique target tensor
+    int fit_index;          // position in the caller's job list
 };
 
 // Offsets of each layer inside the packed parameter vector.

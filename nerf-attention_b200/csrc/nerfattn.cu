@@ -393,6 +393,14 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
                                     double beta1, double beta2, double eps, int32_t first_step,
                                     int32_t precision, void* workspace, size_t workspace_bytes,
                                     na_stream_t stream_) {
+    return nerfattn_fit_batched_ex(fits, nfits, epochs, lr_table, beta1, beta2, eps, first_step, precision, 0, nullptr,
+                                   workspace, workspace_bytes, stream_);
+}
+
+extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int32_t epochs, const double* lr_table,
+                                       double beta1, double beta2, double eps, int32_t first_step,
+                                       int32_t precision, int32_t log_every, float* progress, void* workspace,
+                                       size_t workspace_bytes, na_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     reap_graphs();
     int rc = validate(fits, nfits, precision);
@@ -439,7 +447,7 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
             r.stdv = plan.ustat_std + plan.uniq_stat_off[u];
             r.params = f.params; r.m = f.adam_m; r.v = f.adam_v; r.losses = f.losses;
             r.cos = f.cos_sims; r.ppmse = f.per_pos_mse; r.scalars = f.scalars;
-            r.mean_out = f.mean; r.std_out = f.std; r.omega = f.omega0; r.uniq = u;
+            r.mean_out = f.mean; r.std_out = f.std; r.omega = f.omega0; r.uniq = u; r.fit_index = g.fit_idx[k];
         }
         NA_CUDA_OK(cudaMemcpyAsync(g.d_recs, recs.data(), g.nf * sizeof(FitRec), cudaMemcpyHostToDevice, stream));
     }
@@ -543,6 +551,18 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
         return NA_OK;
     };
 
+    // progress metrics (siren.py:107-115): an fp32 evaluation with the weights epoch e starts from
+    auto log_progress = [&](int e) -> int {
+        if (log_every <= 0 || !progress || (e + 1) % log_every) return NA_OK;
+        float* dst = progress + (size_t)((e + 1) / log_every - 1) * nfits * 2;
+        for (Group& g : plan.groups) {
+            final_eval(g, precision, stream);
+            f32::progress_copy_kernel<<<ceil_div(g.nf, 128), 128, 0, stream>>>(g.d_recs, g.nf, dst);
+            NA_LAUNCH_OK("progress metrics");
+        }
+        return NA_OK;
+    };
+
     if (epochs > 0) {
         const bool use_graph = !env_flag("NERFATTN_NO_GRAPH");
         if (use_graph) {
@@ -564,6 +584,7 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
                 if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
             }
             for (int e = 0; rc == NA_OK && e < epochs; ++e) {
+                if ((rc = log_progress(e))) break;
                 ce = cudaGraphLaunch(exec, stream);
                 if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
             }
@@ -577,6 +598,7 @@ extern "C" int nerfattn_fit_batched(const na_fit_t* fits, int32_t nfits, int32_t
         } else {
             std::vector<cudaStream_t> none; std::vector<cudaEvent_t> nonej;
             for (int e = 0; e < epochs; ++e) {
+                if ((rc = log_progress(e))) return rc;
                 rc = record_epoch(stream, none, nullptr, nonej);
                 if (rc) return rc;
             }

@@ -465,6 +465,14 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     }
 }
 
+// progress metrics of one logging point (siren.py:107-115): scalars[0] = RealMSE, scalars[1] = mean CosSim
+__global__ void progress_copy_kernel(const FitRec* recs, int nf, float* progress) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nf) return;
+    progress[2 * recs[k].fit_index] = recs[k].scalars[0];
+    progress[2 * recs[k].fit_index + 1] = recs[k].scalars[1];
+}
+
 __global__ void tick_kernel(int* epoch) { if (threadIdx.x == 0) *epoch += 1; }
 
 // ---------------------------------------------------------------------------

@@ -11,7 +11,7 @@ import ctypes
 import os
 from pathlib import Path
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'bf16': PREC_BF16}
@@ -47,6 +47,9 @@ _SIGNATURES = {
     'nerfattn_fit_batched': (c_int32, [ctypes.POINTER(NaFit), c_int32, c_int32,
                                        ctypes.POINTER(c_double), c_double, c_double, c_double,
                                        c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    'nerfattn_fit_batched_ex': (c_int32, [ctypes.POINTER(NaFit), c_int32, c_int32,
+                                          ctypes.POINTER(c_double), c_double, c_double, c_double,
+                                          c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     'nerfattn_fit_launch_count': (ctypes.c_longlong, [ctypes.POINTER(NaFit), c_int32, c_int32, c_int32]),
     'nerfattn_forward_workspace_bytes': (c_int32, [ctypes.POINTER(NaFit), c_int32,
                                                    ctypes.POINTER(c_size_t)]),

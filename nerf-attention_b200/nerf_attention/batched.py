@@ -111,7 +111,7 @@ class FitBatch:
 
     def __init__(self, jobs: list[FitJob], epochs: int = 5000, lr: float = 1e-4, device: str = 'cuda',
                  precision: str | None = None, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 keep_initial: bool = False):
+                 keep_initial: bool = False, progress_every: int = 0):
         self.dev = dev = _native.require_cuda(device)
         self.lib = _native.lib()
         self.prec = _native.precision_code(precision)
@@ -186,6 +186,10 @@ class FitBatch:
             self.workspace_bytes = need.value
             self.workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
             self.table = lr_schedule(epochs, lr)
+            # progress metrics (siren.py:107-115): [epochs // every][fit][RealMSE, CosSim]
+            self.progress_every = int(progress_every) if progress_every and epochs >= progress_every > 0 else 0
+            self.progress = (torch.zeros((epochs // self.progress_every) * len(jobs) * 2, dtype=torch.float32, device=dev)
+                             if self.progress_every else None)
         self.flops = [job.config.flops_per_epoch(seq[i], dh[i]) for i, job in enumerate(jobs)]
         stats.setup_seconds = time.perf_counter() - t_wall
         self._t_wall = t_wall
@@ -193,11 +197,12 @@ class FitBatch:
     def launch(self) -> 'FitBatch':
         """Enqueue the whole fit on the current stream (asynchronous)."""
         with torch.cuda.device(self.dev):
-            _native.check(self.lib.nerfattn_fit_batched(
+            _native.check(self.lib.nerfattn_fit_batched_ex(
                 self.fits, len(self.jobs), self.epochs,
                 self.table.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                self.betas[0], self.betas[1], self.eps, 0, self.prec, self.workspace.data_ptr(),
-                self.workspace_bytes, _native.stream_handle()), 'nerfattn_fit_batched')
+                self.betas[0], self.betas[1], self.eps, 0, self.prec, self.progress_every,
+                self.progress.data_ptr() if self.progress is not None else None, self.workspace.data_ptr(),
+                self.workspace_bytes, _native.stream_handle()), 'nerfattn_fit_batched_ex')
         return self
 
     def reset(self) -> None:
@@ -222,7 +227,14 @@ class FitBatch:
         with torch.cuda.device(self.dev):
             h_losses, h_cos, h_ppm, h_scal, h_mean, h_std = (
                 fetch(p) for p in (self.losses, self.cos, self.ppm, self.scal, self.mean, self.std))
+            h_prog = None
+            if self.progress is not None:
+                h_prog = torch.empty(self.progress.numel(), dtype=torch.float32, pin_memory=True)
+                h_prog.copy_(self.progress, non_blocking=True)
+                stats.d2h_bytes += self.progress.numel() * 4
             torch.cuda.current_stream().synchronize()
+        if h_prog is not None:
+            h_prog = h_prog.view(-1, len(jobs), 2)
         if gpu_seconds is not None:
             stats.gpu_seconds = gpu_seconds
         total_flops = float(sum(self.flops)) or 1.0
@@ -237,7 +249,15 @@ class FitBatch:
             fit_losses = h_losses[self.losses.offsets[i]: self.losses.offsets[i] + epochs].tolist()
             raw = n * d * 2                                   # fp16 KV baseline, siren.py:127
             size = job.model.size_bytes()
-            if verbose and epochs:
+            progress = []
+            if h_prog is not None:                           # the reference's progress line, siren.py:112-115
+                step = self.progress_every
+                for k, e in enumerate(range(step, epochs + 1, step)):
+                    progress.append((e, fit_losses[e - 1], float(h_prog[k, i, 0]), float(h_prog[k, i, 1])))
+                    if verbose:
+                        print(f"  Epoch {e}/{epochs} | NormMSE: {fit_losses[e - 1]:.6f} | "
+                              f"RealMSE: {progress[-1][2]:.6f} | CosSim: {progress[-1][3]:.4f}")
+            elif verbose and epochs:
                 step = max(int(log_every), 1)
                 for e in range(step, epochs + 1, step):
                     print(f"  Epoch {e}/{epochs} | NormMSE: {fit_losses[e - 1]:.6f}")
@@ -255,6 +275,7 @@ class FitBatch:
                 train_time_seconds=stats.gpu_seconds * self.flops[i] / total_flops,
                 seq_len=n, d_head=d, num_parameters=p,
             ))
+            results[-1].progress = progress      # [(epoch, NormMSE, RealMSE, CosSim)], siren.py:107-115
         stats.wall_seconds = time.perf_counter() - self._t_wall
         return results
 
@@ -262,13 +283,14 @@ class FitBatch:
 def fit_many(jobs: list[FitJob], epochs: int = 5000, lr: float = 1e-4, device: str = 'cuda',
              log_every: int = 500, verbose: bool = True, precision: str | None = None,
              betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-             keep_optimizer_state: bool = False) -> list[FitResult]:
+             keep_optimizer_state: bool = False, progress: bool | None = None) -> list[FitResult]:
     """Train all jobs for ``epochs`` full-batch Adam steps; one FitResult per job, in order."""
     global last_stats
     if not jobs:
         _native.require_cuda(device)
         return []
-    batch = FitBatch(jobs, epochs=epochs, lr=lr, device=device, precision=precision, betas=betas, eps=eps)
+    batch = FitBatch(jobs, epochs=epochs, lr=lr, device=device, precision=precision, betas=betas, eps=eps,
+                     progress_every=log_every if (verbose if progress is None else progress) else 0)
     with torch.cuda.device(batch.dev):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

@@ -1,0 +1,241 @@
+"""Sequence-length scaling and full-layer profile (reference nerf_attention/experiments/scaling.py).
+
+Same entry points, arguments and result files as the reference, with three differences that
+follow from the batched B200 path:
+
+* every ``medium`` fit of an experiment goes through ONE ``fit_many`` call (the reference loops
+  over ``fit_siren`` serially, scaling.py:160-168 / 404-416): all sequence lengths, layers and
+  key/value tensors train concurrently;
+* the latency columns are measured on the B200: ``siren_time_ms`` keeps the reference protocol
+  (full-sequence forward of one head, 10 warm-ups + 100 timed, scaling.py:225-262);
+  ``hbm_4060_ms`` / ``hbm_h100_ms`` stay the reference's spec arithmetic (``:192-194``) and
+  ``hbm_b200_measured_ms`` / ``siren_decode_qk_ms`` come from the real kernels, batched over
+  ``heads_per_launch`` heads because one head is far below launch latency;
+* real-model extraction is out of scope: ``model_name='synthetic'`` uses the
+  reference's synthetic generator; the structure-analysis columns (``autocorr_*``,
+  ``spectral_*``, reference analyze.py, out of scope) are written as ``None``.
+"""
+
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from nerf_attention import _native
+from nerf_attention.batched import FitJob, fit_many
+from nerf_attention.evaluate import PackedModels, _load_model_from_checkpoint, _time_cuda, kvread_qk
+from nerf_attention.extract import extract_kv_cache_synthetic
+from nerf_attention.types import KVMetadata, SIRENConfig
+
+MEDIUM = SIRENConfig(256, 2, 30.0, 'medium')
+
+
+def _save_scaling_checkpoint(path: Path, name: str, result, seq_len: int) -> None:
+    """The reduced checkpoint variant of the scaling experiment (reference scaling.py:175-187)."""
+    cfg = result.config
+    torch.save({
+        'config': {'hidden_features': cfg.hidden_features, 'hidden_layers': cfg.hidden_layers,
+                   'omega_0': cfg.omega_0, 'name': cfg.name, 'out_features': result.d_head},
+        'model_state': result.model.state_dict(),
+        'target_mean': result.target_mean,
+        'target_std': result.target_std,
+        'metrics': {'name': name, 'config_name': cfg.name, 'seq_len': seq_len,
+                    'raw_size_bytes': result.raw_size_bytes},
+    }, path)
+
+
+def _profile_siren_latency(fits_dir: Path, seq_len: int, device: str) -> float:
+    """Mean full-sequence forward time (ms) over the first 4 checkpoints (reference scaling.py:225-262)."""
+    times = []
+    for mf in sorted(Path(fits_dir).glob('*_model.pt'))[:4]:
+        ckpt = torch.load(mf, map_location='cpu', weights_only=True)
+        model = _load_model_from_checkpoint(ckpt, 'cpu')
+        d = ckpt['config']['out_features']
+        packed = PackedModels([model], seq_len, device=device)
+        out = torch.empty(1, seq_len, d, device=device)
+        times.append(_time_cuda(lambda: packed.forward(out=out), 10, 100) * 1e3)
+    return float(np.mean(times)) if times else 0.0
+
+
+def _decode_latencies(fits_dir: Path, seq_len: int, device: str, heads_per_launch: int, precision: str) -> dict:
+    """Per-head decode cost on the B200, batched: fused SIREN-eval + q.k vs streaming fp16 K from HBM."""
+    files = sorted(Path(fits_dir).glob('*_model.pt'))[:4]
+    if not files:
+        return {}
+    ckpts = [torch.load(f, map_location='cpu', weights_only=True) for f in files]
+    models = [_load_model_from_checkpoint(c, 'cpu') for c in ckpts]
+    d = ckpts[0]['config']['out_features']
+    n = heads_per_launch
+    pick = [i % len(models) for i in range(n)]
+    packed = PackedModels([models[i] for i in pick], seq_len, [ckpts[i]['target_mean'] for i in pick],
+                          [ckpts[i]['target_std'] for i in pick], device)
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(n, d, generator=g).half().to(device)
+    keys = torch.randn(n, seq_len, d, generator=g).half().to(device)
+    scores = torch.empty(n, seq_len, device=device)
+    hbm = _time_cuda(lambda: kvread_qk(keys, q, scores), 5, 30)
+    packed.decode_qk(q, precision, scores)
+    dec = _time_cuda(lambda: packed.decode_qk(q, precision, scores, reuse_setup=True), 5, 30)
+    return {'heads_per_launch': n, 'decode_precision': precision,
+            'hbm_b200_measured_ms': hbm * 1e3 / n, 'siren_decode_qk_ms': dec * 1e3 / n,
+            'hbm_b200_measured_gbs': n * seq_len * d * 2 / hbm / 1e9}
+
+
+def run_scaling_experiment(
+    model_name: str,
+    seq_lengths: list[int],
+    base_dir: Path,
+    device: str = 'cuda',
+    epochs: int = 2000,
+    precision: str | None = None,
+    num_layers: int = 32,
+    num_kv_heads: int = 8,
+    head_dim: int = 128,
+    heads_per_launch: int = 64,
+) -> dict[int, dict]:
+    """Extract + fit + profile at several sequence lengths (reference scaling.py:124-222)."""
+    if model_name != 'synthetic':
+        raise NotImplementedError("real-model KV extraction is out of scope of this build: pass model_name='synthetic'")
+    _native.require_cuda(device)
+    base_dir = Path(base_dir)
+    base_dir.mkdir(parents=True, exist_ok=True)
+    layers = sorted({0, num_layers // 2, num_layers - 1})              # scaling.py:160
+
+    # Phase 1: KV tensors of every length (only the layers that are fitted are written)
+    metadata_map: dict[int, KVMetadata] = {}
+    for seq_len in seq_lengths:
+        kv_dir = base_dir / f'seq_{seq_len}' / 'kv_cache'
+        if (kv_dir / 'metadata.json').exists():                        # idempotent, scaling.py:56-61
+            metadata_map[seq_len] = KVMetadata.from_dict(json.loads((kv_dir / 'metadata.json').read_text()))
+        else:
+            metadata_map[seq_len] = extract_kv_cache_synthetic(seq_len, num_layers, num_kv_heads, head_dim, kv_dir,
+                                                               layers=layers)
+
+    # Phase 2: every medium fit of the experiment in one batched call
+    jobs, where = [], []
+    for seq_len in seq_lengths:
+        kv_dir = base_dir / f'seq_{seq_len}' / 'kv_cache'
+        for layer_idx in layers:
+            data = torch.load(kv_dir / f'layer_{layer_idx:02d}.pt', map_location='cpu', weights_only=True)
+            for kv_type, tensor in (('key', data['keys'][0]), ('value', data['values'][0])):
+                name = f'L{layer_idx}_H0_{kv_type}_medium'
+                jobs.append(FitJob(tensor.contiguous(), MEDIUM, None, name))
+                where.append((seq_len, layer_idx, kv_type, name))
+    print(f'Fitting {len(jobs)} medium SIRENs ({len(seq_lengths)} sequence lengths) in one batched call...')
+    results = fit_many(jobs, epochs=epochs, device=device, log_every=epochs, verbose=False, precision=precision)
+
+    scaling_results: dict[int, dict] = {}
+    for seq_len in seq_lengths:
+        metadata = metadata_map[seq_len]
+        fits_dir = base_dir / f'seq_{seq_len}' / 'fits'
+        fits_dir.mkdir(parents=True, exist_ok=True)
+        fit_results = []
+        for (s, layer_idx, kv_type, name), result in zip(where, results):
+            if s != seq_len:
+                continue
+            fit_results.append({'name': name, 'kv_type': kv_type, 'layer': layer_idx,
+                                'final_cosine_mean': result.final_cosine_mean,
+                                'compression_ratio': result.compression_ratio})
+            _save_scaling_checkpoint(fits_dir / f'{name}_model.pt', name, result, metadata.seq_len)
+            print(f'  seq {seq_len} {name}: CosSim={result.final_cosine_mean:.4f}, '
+                  f'Compress={result.compression_ratio:.1f}x')
+        siren_time_ms = _profile_siren_latency(fits_dir, metadata.seq_len, device)
+        raw_bytes = metadata.seq_len * metadata.head_dim * 2            # KV cache is float16
+        key_r = [r for r in fit_results if r['kv_type'] == 'key']
+        val_r = [r for r in fit_results if r['kv_type'] == 'value']
+        row = {
+            'seq_len': metadata.seq_len,
+            'actual_tokens': metadata.actual_tokens,
+            'autocorr_keys': None, 'autocorr_values': None, 'spectral_keys': None, 'spectral_values': None,
+            'avg_cossim_keys': float(np.mean([r['final_cosine_mean'] for r in key_r])) if key_r else 0.0,
+            'avg_cossim_values': float(np.mean([r['final_cosine_mean'] for r in val_r])) if val_r else 0.0,
+            'avg_compression': float(np.mean([r['compression_ratio'] for r in fit_results])),
+            'siren_time_ms': siren_time_ms,
+            'hbm_4060_ms': raw_bytes / 272e9 * 1000,
+            'hbm_h100_ms': raw_bytes / 3350e9 * 1000,
+            'num_experiments': len(fit_results),
+        }
+        row.update(_decode_latencies(fits_dir, metadata.seq_len, device, heads_per_launch, 'bf16'))
+        scaling_results[seq_len] = row
+        print(f"  seq_len={seq_len}: keys={row['avg_cossim_keys']:.4f}, values={row['avg_cossim_values']:.4f} | "
+              f"SIREN fwd={siren_time_ms:.3f}ms | per head: decode q.k={row.get('siren_decode_qk_ms', 0):.5f}ms, "
+              f"HBM read (B200, measured)={row.get('hbm_b200_measured_ms', 0):.5f}ms")
+
+    with open(base_dir / 'scaling_results.json', 'w') as f:
+        json.dump({str(k): v for k, v in scaling_results.items()}, f, indent=2)
+    with open(base_dir / 'crossover_data.json', 'w') as f:
+        json.dump(crossover_data(scaling_results, head_dim), f, indent=2)
+    return scaling_results
+
+
+def crossover_data(scaling_results: dict[int, dict], head_dim: int = 128) -> dict:
+    """The log-log fit and analytic crossover the reference writes from its plot function
+    (scaling.py:279-291 and the json.dump after it), plus the same with the measured B200 numbers."""
+    seq_lens = sorted(scaling_results)
+    out: dict = {}
+    if len(seq_lens) < 2:
+        return out
+    siren_us = [scaling_results[s]['siren_time_ms'] * 1000 for s in seq_lens]
+    hbm_4060_us = [scaling_results[s]['hbm_4060_ms'] * 1000 for s in seq_lens]
+    a, b = np.polyfit(np.log10(seq_lens), np.log10(siren_us), 1)
+    per_tok_4060 = head_dim * 2 / 272e9 * 1e6
+    per_tok_h100 = head_dim * 2 / 3350e9 * 1e6
+    cross = lambda c: float((c / 10 ** b) ** (1 / (a - 1))) if a != 1 else None     # noqa: E731
+    ratios = [s / h for s, h in zip(siren_us, hbm_4060_us)]
+    out.update({
+        'siren_fit_log_slope': float(a), 'siren_fit_log_intercept': float(b),
+        'siren_scaling': f'time_us ~ n^{a:.3f}', 'hbm_scaling': 'time_us ~ n^1.0 (linear)',
+        'latency_ratio_range': [float(min(ratios)), float(max(ratios))],
+        'crossover_4060_tokens': cross(per_tok_4060), 'crossover_h100_tokens': cross(per_tok_h100),
+    })
+    if all('siren_decode_qk_ms' in scaling_results[s] for s in seq_lens):
+        dec_us = [scaling_results[s]['siren_decode_qk_ms'] * 1000 for s in seq_lens]
+        hbm_us = [scaling_results[s]['hbm_b200_measured_ms'] * 1000 for s in seq_lens]
+        a2, b2 = np.polyfit(np.log10(seq_lens), np.log10(dec_us), 1)
+        per_tok_b200 = float(np.mean([h / s for h, s in zip(hbm_us, seq_lens)]))
+        out.update({
+            'b200_decode_fit_log_slope': float(a2), 'b200_decode_fit_log_intercept': float(b2),
+            'b200_hbm_us_per_token_measured': per_tok_b200,
+            'b200_latency_ratio_range': [float(min(d / h for d, h in zip(dec_us, hbm_us))),
+                                         float(max(d / h for d, h in zip(dec_us, hbm_us)))],
+            'crossover_b200_tokens': (float((per_tok_b200 / 10 ** b2) ** (1 / (a2 - 1)))
+                                      if a2 < 1 else None),
+            'note': 'b200_*: fused SIREN-eval + q.k vs a measured fp16 KV read, both per head, batched launches; '
+                    'no crossover when the decode slope is >= 1',
+        })
+    return out
+
+
+def run_full_layer_profile(
+    kv_dir: Path,
+    output_dir: Path,
+    device: str = 'cuda',
+    epochs: int = 2000,
+    precision: str | None = None,
+) -> list[dict]:
+    """Medium SIREN on ALL layers, head 0, keys + values (reference scaling.py:387-422), one batched call."""
+    kv_dir, output_dir = Path(kv_dir), Path(output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    metadata = KVMetadata.from_dict(json.loads((kv_dir / 'metadata.json').read_text()))
+    jobs, where = [], []
+    for layer_idx in range(metadata.num_layers):
+        path = kv_dir / f'layer_{layer_idx:02d}.pt'
+        if not path.exists():
+            print(f'  Warning: {path} not found, skipping')
+            continue
+        data = torch.load(path, map_location='cpu', weights_only=True)
+        for kv_type, tensor in (('key', data['keys'][0]), ('value', data['values'][0])):
+            jobs.append(FitJob(tensor.contiguous(), MEDIUM, None, f'L{layer_idx}_H0_{kv_type}'))
+            where.append((layer_idx, kv_type))
+    fitted = fit_many(jobs, epochs=epochs, device=device, log_every=epochs, verbose=False, precision=precision)
+    results = []
+    for n, ((layer_idx, kv_type), r) in enumerate(zip(where, fitted), 1):
+        print(f'[{n}/{len(where)}] L{layer_idx}_H0_{kv_type}... CosSim={r.final_cosine_mean:.4f}')
+        results.append({'layer': layer_idx, 'kv_type': kv_type, 'final_cosine_mean': r.final_cosine_mean,
+                        'compression_ratio': r.compression_ratio})
+    with open(output_dir / 'full_layer_profile.json', 'w') as f:
+        json.dump(results, f, indent=2)
+    return results

@@ -117,8 +117,12 @@ def fit_kv_cache(
         fit_jobs[i] = FitJob(job['tensor'], job['config'],
                              SIREN(job['config'], out_features=job['tensor'].shape[1]), job['name'])
 
+    # the fits train concurrently, so the reference's per-fit progress lines (siren.py:112-115) are
+    # collected on the device and printed with each fit's record below
     results = fit_many([fit_jobs[i] for i in mine], epochs=epochs, device=device,
-                       log_every=max(epochs // 5, 100), verbose=False, precision=precision)
+                       log_every=max(epochs // 5, 100), verbose=False, precision=precision,
+                       progress=chatty and not (distributed and world > 1))
+    progress_of = {jobs[i]['name']: getattr(r, 'progress', []) for i, r in zip(mine, results)}
 
     local_records = []
     for i, result in zip(mine, results):
@@ -136,6 +140,8 @@ def fit_kv_cache(
     if chatty:
         for n, r in enumerate(all_records, 1):
             print(f"\n[{n}/{total}] {r['name']}")
+            for e, norm_mse, real_mse, cos in progress_of.get(r['name'], []):
+                print(f"  Epoch {e}/{epochs} | NormMSE: {norm_mse:.6f} | RealMSE: {real_mse:.6f} | CosSim: {cos:.4f}")
             print(f"  -> CosSim: {r['final_cosine_mean']:.4f} | "
                   f"Compress: {r['compression_ratio']:.1f}x | Time: {r['train_time_seconds']:.1f}s")
         with open(output_dir / 'fit_results.json', 'w') as f:

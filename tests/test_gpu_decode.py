@@ -85,3 +85,39 @@ def test_profile_decode_table(cuda_device):
     assert [r['seq_len'] for r in table] == [512, 1024]
     for r in table:
         assert r['kvread_us'] > 0 and r['siren_fp32_us'] > 0 and r['siren_bf16_us'] > 0
+
+
+def test_scaling_experiment_and_layer_profile_outputs(cuda_device, tmp_path):
+    """experiments/scaling.py on the batched path: same files and keys as the reference
+    (scaling.py:124-222, 387-422), plus the measured-B200 columns."""
+    from nerf_attention.experiments import run_full_layer_profile, run_scaling_experiment
+    rows = run_scaling_experiment('synthetic', [256, 512], tmp_path / 'scaling', epochs=40, precision='bf16',
+                                  num_layers=3, num_kv_heads=2, head_dim=128, heads_per_launch=4)
+    saved = json.loads((tmp_path / 'scaling' / 'scaling_results.json').read_text())
+    assert sorted(saved) == ['256', '512'] and sorted(rows) == [256, 512]
+    reference_keys = ['seq_len', 'actual_tokens', 'autocorr_keys', 'autocorr_values', 'spectral_keys', 'spectral_values',
+                      'avg_cossim_keys', 'avg_cossim_values', 'avg_compression', 'siren_time_ms', 'hbm_4060_ms',
+                      'hbm_h100_ms', 'num_experiments']
+    for n in (256, 512):
+        r = saved[str(n)]
+        assert list(r)[:13] == reference_keys                       # reference scaling.py:200-214
+        assert r['num_experiments'] == 6 and r['siren_time_ms'] > 0
+        assert r['hbm_4060_ms'] == pytest.approx(n * 128 * 2 / 272e9 * 1000)
+        assert r['hbm_b200_measured_ms'] > 0 and r['siren_decode_qk_ms'] > 0
+        assert 0.0 < r['avg_cossim_keys'] <= 1.0
+        assert len(list((tmp_path / 'scaling' / f'seq_{n}' / 'fits').glob('*_model.pt'))) == 6
+    ckpt = torch.load(tmp_path / 'scaling' / 'seq_256' / 'fits' / 'L0_H0_key_medium_model.pt', weights_only=True)
+    assert sorted(ckpt) == ['config', 'metrics', 'model_state', 'target_mean', 'target_std']   # scaling.py:175-187
+    assert ckpt['metrics'] == {'name': 'L0_H0_key_medium', 'config_name': 'medium', 'seq_len': 256,
+                               'raw_size_bytes': 256 * 128 * 2}
+    cross = json.loads((tmp_path / 'scaling' / 'crossover_data.json').read_text())
+    assert 'siren_fit_log_slope' in cross and 'b200_decode_fit_log_slope' in cross
+    # the batched call gives the same fits as one fit_siren per tensor would (order / batch independent)
+    data = torch.load(tmp_path / 'scaling' / 'seq_256' / 'kv_cache' / 'layer_00.pt', weights_only=True)
+    torch.manual_seed(123)
+    prof = run_full_layer_profile(tmp_path / 'scaling' / 'seq_256' / 'kv_cache', tmp_path / 'profile', epochs=20,
+                                  precision='bf16')
+    assert [(r['layer'], r['kv_type']) for r in prof] == [(0, 'key'), (0, 'value'), (1, 'key'), (1, 'value'),
+                                                          (2, 'key'), (2, 'value')]
+    assert json.loads((tmp_path / 'profile' / 'full_layer_profile.json').read_text()) == prof
+    assert data['keys'].shape == (2, 256, 128)

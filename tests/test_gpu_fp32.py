@@ -185,3 +185,28 @@ def test_fit_kv_cache_quick_end_to_end(cuda_device, tmp_path, capsys):
 
 def blob_for(kv_dir, layer):
     return torch.load(kv_dir / f'layer_{layer:02d}.pt', weights_only=True)
+
+
+@pytest.mark.parametrize('precision,rtol,cos_atol', [('fp32', 2e-3, 1e-3), ('bf16', 2e-2, 5e-3)])
+def test_progress_metrics_match_reference_logging(cuda_device, capsys, precision, rtol, cos_atol):
+    """siren.py:107-115: every log_every epochs the reference prints NormMSE, RealMSE and CosSim of the
+    prediction made with the weights that epoch starts from.  The batched path evaluates them on the
+    device between graph replays (nerfattn_fit_batched_ex) and prints the same line."""
+    cfg = na.SIRENConfig(128, 2, 30.0, 'kat')
+    kv = smooth_tensor(21, 512, 128)
+    state = seeded_state(cfg, 128, 5)
+    ref = orc.fit(kv, 128, 2, 30.0, epochs=60, lr=1e-4, device='cpu', log_every=20,
+                  init={k: v.clone() for k, v in state.items()})
+    job = na.FitJob(kv, cfg, model_from_state(cfg, 128, state))
+    res = na.fit_many([job], epochs=60, device='cuda', verbose=True, log_every=20, precision=precision)[0]
+    assert [p[0] for p in res.progress] == [p[0] for p in ref.progress] == [20, 40, 60]
+    for got, want in zip(res.progress, ref.progress):
+        assert got[1] == pytest.approx(want[1], rel=rtol)            # NormMSE
+        assert got[2] == pytest.approx(want[2], rel=rtol)            # RealMSE
+        assert abs(got[3] - want[3]) <= cos_atol                     # CosSim
+    out = capsys.readouterr().out
+    assert f'  Epoch 40/60 | NormMSE: {res.progress[1][1]:.6f} | RealMSE: {res.progress[1][2]:.6f} | CosSim: {res.progress[1][3]:.4f}' in out
+    # quiet runs do not pay for the evaluations
+    quiet = na.fit_many([na.FitJob(kv, cfg, model_from_state(cfg, 128, state))], epochs=60, device='cuda',
+                        verbose=False, precision=precision)[0]
+    assert quiet.progress == [] and quiet.losses == res.losses

@@ -235,3 +235,18 @@ def test_no_cpu_fallback():
     for src in pkg.glob('*.py'):
         assert 'oracle' not in src.read_text().replace('siren_oracle', 'oracle') or src.name == '__init__.py', \
             f'{src.name} must not reference the oracle'
+
+
+def test_crossover_fit_reproduces_reference_published_numbers():
+    """experiments.scaling.crossover_data against the reference's own committed results: its
+    scaling_results.json latency columns in, its crossover_data.json out (scaling.py:279-291)."""
+    from nerf_attention.experiments.scaling import crossover_data
+    gold = json.loads((Path(__file__).parent / 'golden' / 'reference_scaling.json').read_text())
+    rows = {int(k): v for k, v in gold['scaling_results'].items()}
+    got, want = crossover_data(rows), gold['crossover_data']
+    assert got['siren_fit_log_slope'] == pytest.approx(want['siren_fit_log_slope'], rel=1e-9)
+    assert got['siren_fit_log_intercept'] == pytest.approx(want['siren_fit_log_intercept'], rel=1e-9)
+    assert got['latency_ratio_range'] == pytest.approx(want['latency_ratio_range'], rel=1e-9)
+    assert got['crossover_4060_tokens'] == pytest.approx(want['crossover_4060_tokens'], rel=1e-6)
+    assert got['crossover_h100_tokens'] == pytest.approx(want['crossover_h100_tokens'], rel=1e-6)
+    assert got['siren_scaling'] == want['siren_scaling']
