@@ -161,15 +161,30 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         g.dy = ar.take<char>(nd * esz);
         g.yeval = ar.take<float>(nd);
         if (bf) { g.evalact[0] = ar.take<float>(nh); g.evalact[1] = ar.take<float>(nh); }
-        // split-K of dW so that the launch has >= ~2 waves of CTAs (fp32 path only)
-        int out_tiles = 0;
-        for (int l = 1; l <= g.L + 1; ++l)
+        g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
+        // split-K of dW so that the launch fills the GPU: ~2 waves of CTAs on the fp32 path.  On the chain path
+        // it is available for small groups whose dW GEMMs have fewer output tiles than SMs (NERFATTN_DW_SPLIT=1)
+        // but off by default: measured 0.461 vs 0.450 ms per epoch for the dW phase of the 280-fit sweep -- the
+        // small groups' kernels already overlap with the other groups' on the graph's parallel branches
+        int out_tiles = 0, out_tiles_min = 1 << 30;
+        for (int l = 1; l <= g.L + 1; ++l) {
             out_tiles = std::max(out_tiles, ceil_div(g.lm.out_dim[l], 128) * ceil_div(g.lm.in_dim[l], 128));
-        int want = bf ? 1 : std::max(1, (2 * 148 * 2) / std::max(1, g.nf * out_tiles));
-        int max_split = std::max(1, g.N / 256);
-        g.nsplit = std::min(want, max_split);
-        g.ksplit = (int)align_up((size_t)ceil_div(g.N, g.nsplit), 16);
-        g.nsplit = ceil_div(g.N, g.ksplit);
+            out_tiles_min = std::min(out_tiles_min, ceil_div(g.lm.out_dim[l], 128) * (g.H / tc::dw_bn(g.H)));
+        }
+        if (bf) {
+            g.nsplit = 1;
+            if (g.use_chain && env_flag("NERFATTN_DW_SPLIT"))
+                while (g.nsplit < 4 && g.nsplit * 2 <= g.mtiles && g.nf * out_tiles_min * g.nsplit * 2 <= 148 + 74 &&
+                       (g.N / 64) % (g.nsplit * 2) == 0)
+                    g.nsplit *= 2;
+            g.ksplit = g.N / g.nsplit;
+        } else {
+            int want = std::max(1, (2 * 148 * 2) / std::max(1, g.nf * out_tiles));
+            int max_split = std::max(1, g.N / 256);
+            g.nsplit = std::min(want, max_split);
+            g.ksplit = (int)align_up((size_t)ceil_div(g.N, g.nsplit), 16);
+            g.nsplit = ceil_div(g.N, g.ksplit);
+        }
         g.gradpart = ar.take<float>((size_t)g.nsplit * g.nf * g.lm.P);
         size_t coff = 0;
         for (int l = 0; l <= g.L + 1; ++l) {
@@ -178,7 +193,6 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         }
         g.colpart = ar.take<float>(coff);
         g.xpart = ar.take<float>((size_t)g.nf * g.mtiles * g.H);
-        g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
         g.losspart_per_fit = g.use_chain ? chain::loss_partials_per_fit(g.N, g.H)
                              : bf ? tc::loss_partials_per_fit(g.N, g.D) : g.mtiles * ceil_div(g.D, 128);
         g.losspart = ar.take<float>((size_t)g.nf * g.losspart_per_fit);
@@ -255,7 +269,7 @@ static void launch_adam(const Group& g, const Plan& plan, double beta1, double b
     a.gradpart = g.gradpart; a.grad_split_stride = (size_t)g.nf * g.lm.P; a.grad_fit = g.lm.P; a.nsplit = g.nsplit;
     a.colpart = g.colpart;
     for (int l = 0; l < kMaxLayers; ++l) a.colpart_layer_off[l] = g.colpart_layer_off[l];
-    for (int l = 0; l < kMaxLayers; ++l) a.col_mt[l] = (g.wbf16 && l > 0) ? 1 : g.mtiles;
+    for (int l = 0; l < kMaxLayers; ++l) a.col_mt[l] = (g.wbf16 && l > 0) ? g.nsplit : g.mtiles;
     a.xpart = g.xpart;
     a.losspart = g.losspart; a.losspart_per_fit = g.losspart_per_fit;
     a.loss_inv_count = 1.0f / ((float)g.N * (float)g.D);
@@ -536,7 +550,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
                 int r2 = g.use_chain
                     ? chain::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, *g.cmaps, g.act, g.cosb, g.dy,
                                    g.chain_scratch, g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                   g.losspart_per_fit, g.mtiles, af, s)
+                                   g.losspart_per_fit, g.mtiles, af, g.nsplit, s)
                     : tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
                                 g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
                                 g.losspart_per_fit, g.mtiles, s);

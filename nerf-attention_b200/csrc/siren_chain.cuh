@@ -673,7 +673,7 @@ inline bool adam_fused() { const char* e = getenv("NERFATTN_ADAM_FUSED"); return
 inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const GroupMaps& m,
                  const ChainMaps& cm, void* const* act, void* const* dzs, void* dy, __nv_bfloat16* scratch,
                  float* gradpart, float* colpart, const size_t* colpart_layer_off, float* xpart, float* losspart,
-                 int losspart_per_fit, int mtiles, const AdamFuse& af, cudaStream_t s) {
+                 int losspart_per_fit, int mtiles, const AdamFuse& af, int ksplits, cudaStream_t s) {
     int rc;
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
@@ -694,8 +694,9 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
         TcArgs w = base;
         w.M = width; w.N = H; w.K = N;
         w.fout = gradpart; w.fout_fit = lm.P; w.fout_off = lm.w_off[l]; w.ldf = H;
-        w.biasgrad = colpart + colpart_layer_off[l]; w.biasgrad_fit = width;
-        if (af.epoch && (phases & 4)) {
+        w.biasgrad = colpart + colpart_layer_off[l]; w.biasgrad_fit = (size_t)ksplits * width;
+        w.ksplits = ksplits; w.fout_split = (size_t)nf * lm.P;
+        if (af.epoch && (phases & 4) && ksplits == 1) {
             w.adam_epoch = af.epoch; w.adam_step_size = af.step_size; w.adam_bc2 = af.bc2;
             w.adam_beta1 = af.beta1; w.adam_beta2 = af.beta2; w.adam_eps = af.eps;
             w.adam_w_off = lm.w_off[l]; w.adam_b_off = lm.b_off[l];

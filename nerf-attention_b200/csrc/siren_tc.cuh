@@ -58,7 +58,8 @@ struct TcArgs {
     __nv_bfloat16* out1; size_t out1_fit;                 // cos_l
     const __nv_bfloat16* cprev; size_t cprev_fit;         // kDx: cos_{l-1}
     float* fout; size_t fout_fit; int fout_off; int ldf;  // kRaw: C; kDw: gradpart + w_off
-    float* biasgrad; size_t biasgrad_fit;                 // kDw: db_l [nb][M]
+    float* biasgrad; size_t biasgrad_fit;                 // kDw: db_l [nb][ksplits][M]
+    int ksplits; size_t fout_split;                       // kDw: split-K (partials [ksplits][...], summed by Adam)
     float* losspart; int losspart_per_fit;                // kFwdOut
     float loss_scale;
     // kDw with Adam fused into the epilogue (chain mode): the gradient tile goes straight from TMEM into
@@ -221,8 +222,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = g.K / BK;
-    const int total_tiles = g.nb * g.m_tiles * g.n_tiles;
+    // split-K (kDw of small groups: one output tile per fit would leave most SMs idle): tile index
+    // = (fit, m tile, n tile, K slice), partial results go to separate slots and are summed by Adam
+    const int ksplits = (MODE == kDw && g.ksplits > 1) ? g.ksplits : 1;
+    const int num_kb = g.K / BK / ksplits;
+    const int total_tiles = g.nb * g.m_tiles * g.n_tiles * ksplits;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -251,10 +255,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % g.n_tiles, mt = (tile / g.n_tiles) % g.m_tiles, b = tile / (g.n_tiles * g.m_tiles);
+                const int ks = tile % ksplits, t2 = tile / ksplits;
+                const int nt = t2 % g.n_tiles, mt = (t2 / g.n_tiles) % g.m_tiles, b = t2 / (g.n_tiles * g.m_tiles);
                 const int a_boxes = A_MN ? min(2, ceil_div(g.M - mt * BM, 64)) : 1;
                 const uint32_t tx_bytes = (A_MN ? a_boxes * 8192 : A_STAGE_BYTES) + C::B_STAGE_BYTES;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = ks * num_kb; kb < (ks + 1) * num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], tx_bytes);
                     uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
@@ -292,7 +297,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const uint64_t odesc0 = make_desc(smem_u32(smem_ones), 0, 1024);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;     // kb counts within this tile's K slice
                         tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * A_KADV), bdesc0 + (uint64_t)(k * B_KADV), idesc, acc);
                         if (MODE == kDw)
                             tc_mma_bf16(d_tmem + BN, adesc0 + (uint64_t)(k * A_KADV), odesc0 + (uint64_t)(k * 2), idesc_ones, acc);
@@ -312,7 +317,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         constexpr bool kHeavy = (MODE == kFwdSine || MODE == kFwdDot);   // big inlined bodies: keep the chunk loop rolled
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int nt = tile % g.n_tiles, mt = (tile / g.n_tiles) % g.m_tiles, b = tile / (g.n_tiles * g.m_tiles);
+            const int ks = tile % ksplits, t2 = tile / ksplits;
+            const int nt = t2 % g.n_tiles, mt = (t2 / g.n_tiles) % g.m_tiles, b = t2 / (g.n_tiles * g.m_tiles);
             const int as = iter % NACC; const uint32_t aphase = (iter / NACC) & 1;
             const int row = mt * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
@@ -386,7 +392,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 } else if (MODE == kRaw || MODE == kDw) {
                     if (row_ok) {
-                        float* dst = g.fout + (size_t)b * g.fout_fit + g.fout_off + (size_t)row * g.ldf + col;
+                        float* dst = g.fout + (size_t)ks * g.fout_split + (size_t)b * g.fout_fit + g.fout_off + (size_t)row * g.ldf + col;
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) st_global_256(dst + j, &v[j]);
                     }
@@ -517,7 +523,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), adam_bc2v), g.adam_eps);
                         ww = __fadd_rn(ww, __fdiv_rn(__fmul_rn(adam_nss, mm), denom));
                         rec->m[pi] = mm; rec->v[pi] = vv; rec->params[pi] = ww;
-                    } else g.biasgrad[(size_t)b * g.biasgrad_fit + row] = __uint_as_float(dbv);
+                    } else g.biasgrad[(size_t)b * g.biasgrad_fit + (size_t)ks * g.M + row] = __uint_as_float(dbv);
                 }
             }
             if (MODE == kFwdDot && row_ok)     // this thread's row, this warp's half of the tile's columns
@@ -708,7 +714,7 @@ inline int launch_occ(const GemmMaps& maps, TcArgs a, cudaStream_t s) {
     constexpr int smem = smem_bytes<BN, OCC>();
     a.m_tiles = ceil_div(a.M, BM);
     a.n_tiles = a.N / BN;
-    const int tiles = a.nb * a.m_tiles * a.n_tiles;
+    const int tiles = a.nb * a.m_tiles * a.n_tiles * ((MODE == kDw && a.ksplits > 1) ? a.ksplits : 1);
     const int grid = std::min(tiles, num_sms() * OCC);
     tc_gemm_kernel<MODE, A_MN, B_MN, BN, OCC><<<grid, NTHREADS, smem, s>>>(maps.a, maps.b, a);
     cudaError_t e = cudaGetLastError();
