@@ -207,7 +207,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     uint64_t* empty = bars + STAGES;             // [STAGES]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * STAGES;      // [2]       accumulator of the slot complete
     uint64_t* act_ready = bars + 2 * STAGES + 2; // [2]       A operand of the slot written, accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* buf_free = bars + 2 * STAGES + 4;  // [2]       the TMA store of the slot's operand buffer has read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = g.L, D = g.D;
@@ -217,7 +218,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) { printf("nerfattn: chain smem base not 1024-aligned\n"); __trap(); }
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], C::EPW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], C::EPW); mbar_init(&buf_free[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -307,13 +308,11 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (+ TMA stores of the finished operand buffers)
-        // Step s consumes what the epilogue wrote in step s-1: it first TMA-stores that buffer to
-        // global (h_l / dY / dz_l, the dW operands), then contracts it.  Step `nsteps` only stores
-        // (dz_0) and hands the buffer back.  acc_full[slot] = accumulator complete AND buffer free.
+        // ===================================================== MMA issuer
+        // Step s contracts what the epilogue wrote in step s-1 (warp 2 stores the same buffer to global
+        // meanwhile).  Step `nsteps` has no MMA: the wait only keeps the barrier phases in step.
         int stage = 0; uint32_t phase = 0;
         uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot]
-        const uint64_t pol_stream = policy_evict_first();   // h_l / dz_l / dY are read by a later kernel: do not displace the cos scratch
         for (int round = 0;; ++round) {
             if (tile_of(round, 0) >= total_tiles) break;
             for (int s = 1; s <= (FWD ? nsteps - 1 : nsteps); ++s) {
@@ -321,27 +320,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 const uint32_t idesc = make_idesc(st.n, false, st.mn != 0);
                 const uint32_t b_lbo = st.mn ? 8192u : 0u;
                 const uint32_t b_kadv = st.mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-                // what the epilogue produced in step s-1
-                const int ps = s - 1;
-                const CUtensorMap* omap = (ps <= L) ? &maps.hout[ps] : (ps == L + 1) ? &maps.yout : &maps.zout[2 * L + 2 - ps];
-                const int ochunks = (ps == L + 1) ? D / 64 : H / 64;
                 for (int slot = 0; slot < NSLOT; ++slot) {
                     const int tile = tile_of(round, slot);
                     if (tile >= total_tiles) break;
-                    const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
                     mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
                     rdy_phase ^= 1u << slot;
                     tc_fence_after();
                     uint8_t* const act = smem + slot * C::ACT_BYTES;
-                    if (!FWD && lane == 0 && !(g.dbg & 1)) {
-                        for (int kc = 0; kc < ochunks; ++kc) tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, mt * BM, fit, pol_stream);
-                        tma_store_commit();
-                    }
-                    if (s == nsteps) {
-                        if (lane == 0) { tma_store_wait_read(); mbar_arrive(&acc_full[slot]); }
-                        __syncwarp();
-                        continue;
-                    }
+                    if (s == nsteps) continue;
                     const uint32_t act_u32 = smem_u32(act);
                     for (int np = 0; np < st.nparts; ++np) {
                         const uint32_t d_tmem = tmem_base + slot * C::ACC_COLS + np * 256;
@@ -356,15 +342,44 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                                     tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
                                                 (kc > 0 || k > 0) ? 1u : 0u);
                                 if (CL == 2) tc_commit_mc(&empty[stage], 3); else tc_commit(&empty[stage]);
-                                if (np == st.nparts - 1 && kc == st.kch - 1) {
-                                    if (!FWD) tma_store_wait_read();  // the store has read the buffer long before the MMAs retire
-                                    tc_commit(&acc_full[slot]);
-                                }
+                                if (np == st.nparts - 1 && kc == st.kch - 1) tc_commit(&acc_full[slot]);
                             }
                             __syncwarp();
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
+                }
+            }
+        }
+    } else if (warp == 2 && !FWD) {
+        // ===================================================== store warp: every finished operand buffer is also a dW
+        // operand (h_l / dY / dz_l): TMA-store it to global while the tensor core contracts it, and tell the
+        // epilogue when the store has read the buffer (its own warp, so that this wait never delays an MMA)
+        uint32_t rdy_phase = 0;
+        const uint64_t pol_stream = policy_evict_first();   // read by a later kernel: do not displace the cos scratch
+        for (int round = 0;; ++round) {
+            if (tile_of(round, 0) >= total_tiles) break;
+            for (int s = 1; s <= nsteps; ++s) {
+                const int ps = s - 1;                                // the step whose output is stored
+                const CUtensorMap* omap = (ps <= L) ? &maps.hout[ps] : (ps == L + 1) ? &maps.yout : &maps.zout[2 * L + 2 - ps];
+                const int ochunks = (ps == L + 1) ? D / 64 : H / 64;
+                for (int slot = 0; slot < NSLOT; ++slot) {
+                    const int tile = tile_of(round, slot);
+                    if (tile >= total_tiles) break;
+                    const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
+                    mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
+                    rdy_phase ^= 1u << slot;
+                    if (lane == 0) {
+                        if (!(g.dbg & 1)) {
+                            const uint8_t* act = smem + slot * C::ACT_BYTES;
+                            for (int kc = 0; kc < ochunks; ++kc)
+                                tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, ((g.dbg & 4) ? (int)(blockIdx.x % g.mtiles) : mt) * BM, (g.dbg & 4) ? 0 : fit, pol_stream);
+                            tma_store_commit();
+                            tma_store_wait_read();
+                        }
+                        mbar_arrive(&buf_free[slot]);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -387,7 +402,15 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
         const uint32_t t_row = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + col0;
         __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H) + (size_t)r * H + col0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, free_phase = 0;
+#ifdef NA_CHAIN_TIMING
+        long long t_acc = 0, t_kind[4] = {0, 0, 0, 0}, t_begin = clock64(), tq = 0, ts = 0, t_acc0 = 0;
+#define NA_T0() tq = clock64()
+#define NA_T1() t_acc += clock64() - tq
+#else
+#define NA_T0()
+#define NA_T1()
+#endif
         for (int round = 0;; ++round) {
             const int tile = tile_of(round, slot);
             if (tile >= total_tiles) break;
@@ -396,9 +419,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             const int row = mt * BM + r;
             const float omega = rec->omega;
             for (int s = 0; s < nsteps; ++s) {
+#ifdef NA_CHAIN_TIMING
+                ts = clock64(); t_acc0 = t_acc;
+#endif
                 if (s == 0) {
                     // the buffer is free once the MMA warp has stored the previous tile's dz_0
-                    if (!FWD && round > 0) { mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1; }
+                    if (!FWD && round > 0) { NA_T0(); mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; NA_T1(); }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
                     const float x = __ldg(rec->pos + row);
                     const float* w0 = rec->params + g.w_off[0] + col0;
@@ -436,7 +462,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     float4 bn[4];                                // bias of the next 16 columns (L1-resident)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc) + j);
-                    mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
+                    NA_T1();
                     tc_fence_after();
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
                     uint32_t v[16];
@@ -493,7 +521,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     uint32_t ta[16], tb[16];                     // targets of this unit and the next: two units in flight
                     ld_global_nc_na_256(tn, &ta[0]); ld_global_nc_na_256(tn + 8, &ta[8]);
                     if (nuo > 1) { ld_global_nc_na_256(tn + 16, &tb[0]); ld_global_nc_na_256(tn + 24, &tb[8]); }
-                    mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
+                    NA_T1();
                     tc_fence_after();
                     const uint32_t t_out = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + ocol0;
                     float sq = 0.f;
@@ -531,7 +561,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     uint32_t cc[PFD][8];
 #pragma unroll
                     for (int p = 0; p < PFD; ++p) ld_global_256_hint(csrc + p * 16, cc[p], pol_keep);
-                    mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
+                    if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
+                    NA_T1();
                     tc_fence_after();
                     uint32_t va[16], vb[16];
                     tmem_ld16(t_row, va);
@@ -553,6 +585,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     }
                 }
                 // operand buffer complete: hand it to the MMA warp (stores it to global, then contracts it)
+#ifdef NA_CHAIN_TIMING
+                t_kind[s == 0 ? 0 : s <= L ? 1 : s == L + 1 ? 2 : 3] += (clock64() - ts) - (t_acc - t_acc0);
+#endif
                 if (FWD && s == nsteps - 1) { tc_fence_before(); continue; }     // nothing consumes the last forward step
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
                 tc_fence_before();
@@ -560,6 +595,11 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 if (lane == 0) mbar_arrive(&act_ready[slot]);
             }
         }
+#ifdef NA_CHAIN_TIMING
+        if (lane == 0 && (ei == 0 || ei == 5) && (blockIdx.x == 0 || blockIdx.x == 77))
+            printf("chain timing cta %d slot %d warp %d: total %lld wait_acc %lld E0 %lld sine %lld out %lld dx %lld\n", (int)blockIdx.x,
+                   slot, ei, clock64() - t_begin, t_acc, t_kind[0], t_kind[1], t_kind[2], t_kind[3]);
+#endif
     }
 
     tc_fence_before();
