@@ -310,7 +310,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     } else if (warp == 1) {
         // ===================================================== MMA issuer
         // Step s contracts what the epilogue wrote in step s-1 (warp 2 stores the same buffer to global
-        // meanwhile).  Step `nsteps` has no MMA: the wait only keeps the barrier phases in step.
+        // meanwhile).  Step `nsteps` has no MMA: it only acknowledges the phase (see below).
         int stage = 0; uint32_t phase = 0;
         uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot]
         for (int round = 0;; ++round) {
@@ -327,7 +327,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     rdy_phase ^= 1u << slot;
                     tc_fence_after();
                     uint8_t* const act = smem + slot * C::ACT_BYTES;
-                    if (s == nsteps) continue;
+                    if (s == nsteps) {
+                        // No MMA: acknowledge the phase.  The next tile's E0 waits for this, otherwise a fast slot could
+                        // complete act_ready twice before this warp looked at it (parity waits alias after two phases).
+                        if (lane == 0) mbar_arrive(&acc_full[slot]);
+                        __syncwarp();
+                        continue;
+                    }
                     const uint32_t act_u32 = smem_u32(act);
                     for (int np = 0; np < st.nparts; ++np) {
                         const uint32_t d_tmem = tmem_base + slot * C::ACC_COLS + np * 256;
@@ -424,7 +430,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #endif
                 if (s == 0) {
                     // the buffer is free once the MMA warp has stored the previous tile's dz_0
-                    if (!FWD && round > 0) { NA_T0(); mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; NA_T1(); }
+                    if (!FWD && round > 0) {
+                        NA_T0();
+                        mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;       // the MMA warp has seen the last step
+                        mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1;     // the store warp has stored dz_0
+                        NA_T1();
+                    }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
                     const float x = __ldg(rec->pos + row);
                     const float* w0 = rec->params + g.w_off[0] + col0;
