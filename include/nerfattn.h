@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NERFATTN_ABI_VERSION 6
+#define NERFATTN_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define NA_API __attribute__((visibility("default")))
@@ -179,6 +179,26 @@ NA_API int nerfattn_decode_qk(const na_fit_t* key_models, int32_t n, const void*
  */
 NA_API int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float* scores,
                        int32_t n, int32_t N, int32_t D, na_stream_t stream);
+
+/*
+ * Single-query attention over the cached positions (the decode integration the reference describes
+ * in README.md:3-8 and never builds):
+ *   scores = nerfattn_decode_qk / nerfattn_kvread_qk,  p = softmax(scale * scores),  out = sum_t p_t V_t.
+ *
+ * nerfattn_softmax     p[i][:] = softmax(scale * scores[i][:]) in place, scores DEVICE fp32 [n][N]
+ * nerfattn_kvread_pv   baseline: out[i] = sum_t p[i][t] V[i][t][:], V DEVICE fp16 [n][N][D] streamed from HBM
+ * nerfattn_decode_pv   the same with V_i(t) = SIREN_i(position t) * std_i + mean_i (value models); in the
+ *                      BF16 mode V is never materialised: the fused forward kernel reduces p_t * h_L(t)
+ *                      over the positions and the output layer is applied once to the H-vector
+ * out: DEVICE fp32 [n][D].  Workspaces: nerfattn_pv_workspace_bytes (models == NULL: the kvread variant).
+ */
+NA_API int nerfattn_softmax(float* scores, int32_t n, int32_t N, float scale, na_stream_t stream);
+NA_API int nerfattn_pv_workspace_bytes(const na_fit_t* value_models, int32_t n, int32_t N, int32_t D,
+                                int32_t precision, size_t* bytes);
+NA_API int nerfattn_kvread_pv(const void* v_fp16, const float* p, float* out, int32_t n, int32_t N, int32_t D,
+                       void* workspace, size_t workspace_bytes, na_stream_t stream);
+NA_API int nerfattn_decode_pv(const na_fit_t* value_models, int32_t n, const float* p, float* out,
+                       int32_t precision, void* workspace, size_t workspace_bytes, na_stream_t stream);
 
 /*
  * Diagnostic: C[M,N] (fp32) = A x B with BF16 operands through the same

@@ -116,5 +116,105 @@ l0dot_kernel(const FitRec* recs, int N, int H, const float* u, const float* c0, 
     if (lane == 0) scores[blockIdx.y][row] = s + c0[blockIdx.y];
 }
 
+// ---------------------------------------------------------------------------
+// Attention over the cached positions for one new token (the decode integration the
+// reference describes, README.md:3-8, but never builds).  scores -> softmax -> sum_t p_t V_t.
+
+// p[i][:] = softmax(scale * scores[i][:]) in place; one block per head.
+__global__ void __launch_bounds__(1024) softmax_kernel(float* s, int N, float scale) {
+    __shared__ float red[32];
+    float* row = s + (size_t)blockIdx.x * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float m = -3.0e38f;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) m = fmaxf(m, row[t] * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float l = 0.f;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) { const float e = expf(row[t] * scale - m); row[t] = e; l += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) red[warp] = l;
+    __syncthreads();
+    l = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) l += red[w];             // fixed order: deterministic
+    const float inv = 1.0f / l;
+    for (int t = threadIdx.x; t < N; t += blockDim.x) row[t] *= inv;
+}
+
+// partial[i][c][d] = sum_{t in chunk c} p[i][t] V[i][t][d]; V streamed once (fp16 KV cache, or the fp32
+// reconstruction of the fp32 SIREN path).  256 rows per chunk, D/8 lanes per row, 16/32-byte loads.
+constexpr int kPvChunk = 256;
+template <typename T>
+__global__ void __launch_bounds__(256) pv_kernel(const T* __restrict__ V, const float* __restrict__ p, float* __restrict__ partial,
+                                                 int N, int D, int chunks) {
+    extern __shared__ float pv_red[];                    // [256 / LG][D]
+    const int LG = D / 8, rows_per_pass = 256 / LG;
+    const int lg = threadIdx.x % LG, rp = threadIdx.x / LG;
+    const int i = blockIdx.y, c = blockIdx.x;
+    const int t0 = c * kPvChunk, t1 = min(N, t0 + kPvChunk);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int t = t0 + rp; t < t1; t += rows_per_pass) {
+        const float w = __ldg(p + (size_t)i * N + t);
+        const T* src = V + ((size_t)i * N + t) * D + lg * 8;
+        if constexpr (sizeof(T) == 2) {
+            uint32_t v[4];
+            asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(src));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[k]));
+                acc[2 * k] = fmaf(w, f.x, acc[2 * k]); acc[2 * k + 1] = fmaf(w, f.y, acc[2 * k + 1]);
+            }
+        } else {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+            acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pv_red[rp * D + lg * 8 + k] = acc[k];
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < rows_per_pass; ++q) s += pv_red[q * D + d];
+        partial[((size_t)i * chunks + c) * D + d] = s;
+    }
+}
+__global__ void pv_finish_kernel(const float* partial, int chunks, int D, float* out) {
+    const int i = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += partial[((size_t)i * chunks + c) * D + d];
+        out[(size_t)i * D + d] = s;
+    }
+}
+
+// SIREN values, tensor path: g = sum of the chain kernel's per-warp partial sums of p_t * h_L(t) (fixed order),
+// then out = std * (Wf g + bf) + mean  (sum_t p_t = 1): V is never materialised.
+__global__ void __launch_bounds__(256)
+attn_finish_kernel(const FitRec* recs, const float* pvpart, int nparts, int H, int D, int wf_off, int bf_off, float* out) {
+    extern __shared__ float gsum[];                      // [H]
+    const FitRec& rec = recs[blockIdx.x];
+    const float* part = pvpart + (size_t)blockIdx.x * nparts * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nparts; ++k) s += part[(size_t)k * H + j];
+        gsum[j] = s;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float* w = rec.params + wf_off + (size_t)d * H;
+        float s = 0.f;
+        for (int j = 0; j < H; ++j) s = fmaf(w[j], gsum[j], s);
+        out[(size_t)blockIdx.x * D + d] = fmaf(rec.stdv[d], s + rec.params[bf_off + d], rec.mean[d]);
+    }
+}
+
 }  // namespace dec
 }  // namespace na

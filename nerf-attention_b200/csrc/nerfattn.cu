@@ -826,6 +826,135 @@ extern "C" int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float*
     return NA_OK;
 }
 
+// =========================================================================== attention decode (softmax, P.V)
+namespace na {
+struct PvPlan {
+    Group g;
+    float* partial;        // kvread / fp32: [n][chunks][D];  bf16 chain: [n][N/32][H]
+    int chunks;
+    float* vfull;          // fp32 mode: reconstructed values [n][N][D]
+    float** d_out;         // fp32 mode: per-model output pointers into vfull
+    bool chain;
+    size_t bytes;
+};
+static void pv_plan(const na_fit_t* m, int n, int N, int D, int precision, void* ws, PvPlan& p) {
+    Arena ar(ws);
+    p = PvPlan{};
+    p.chunks = ceil_div(N, dec::kPvChunk);
+    if (!m) {                                           // KV-read baseline
+        p.partial = ar.take<float>((size_t)n * p.chunks * D);
+        p.bytes = ar.bytes();
+        return;
+    }
+    Group& g = p.g;
+    g.N = m[0].N; g.D = m[0].D; g.H = m[0].H; g.L = m[0].L; g.nf = n;
+    g.lm = make_layer_map(g.H, g.L, g.D);
+    g.mtiles = ceil_div(g.N, 128);
+    p.chunks = ceil_div(g.N, dec::kPvChunk);
+    g.d_recs = ar.take<FitRec>(n);
+    p.chain = precision == NA_PREC_BF16 && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
+    if (p.chain) {
+        g.wbf16 = ar.take<__nv_bfloat16>((size_t)n * g.lm.P);
+        p.partial = ar.take<float>((size_t)n * (g.N / 32) * g.H);
+    } else {
+        const size_t nh = (size_t)n * g.N * g.H;
+        g.act[0] = ar.take<char>(nh * 4);
+        g.act[1] = ar.take<char>(nh * 4);
+        p.vfull = ar.take<float>((size_t)n * g.N * g.D);
+        p.d_out = ar.take<float*>(n);
+        p.partial = ar.take<float>((size_t)n * p.chunks * g.D);
+    }
+    p.bytes = ar.bytes();
+}
+}  // namespace na
+
+extern "C" int nerfattn_softmax(float* scores, int32_t n, int32_t N, float scale, na_stream_t stream_) {
+    if (!scores || n <= 0 || N <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    dec::softmax_kernel<<<n, 1024, 0, (cudaStream_t)stream_>>>(scores, N, scale);
+    NA_LAUNCH_OK("softmax_kernel");
+    return NA_OK;
+}
+
+extern "C" int nerfattn_pv_workspace_bytes(const na_fit_t* models, int32_t n, int32_t N, int32_t D, int32_t precision,
+                                           size_t* bytes) {
+    if (!bytes || n <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    if (models) {
+        int rc = infer_validate(models, n, true);
+        if (rc) return rc;
+        N = models[0].N; D = models[0].D;
+    }
+    if (N <= 0 || D <= 0 || D % 8) { set_error("pv: D must be a positive multiple of 8"); return NA_ERR_UNSUPPORTED; }
+    PvPlan p; pv_plan(models, n, N, D, precision, nullptr, p);
+    *bytes = p.bytes;
+    return NA_OK;
+}
+
+extern "C" int nerfattn_kvread_pv(const void* v_fp16, const float* p, float* out, int32_t n, int32_t N, int32_t D,
+                                  void* workspace, size_t workspace_bytes, na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!v_fp16 || !p || !out || n <= 0 || N <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    if (D <= 0 || D % 8 || 256 % (D / 8)) { set_error("pv: D must be 8, 16, .., 2048 with D/8 dividing 256"); return NA_ERR_UNSUPPORTED; }
+    if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return NA_ERR_WORKSPACE; }
+    PvPlan pl; pv_plan(nullptr, n, N, D, 0, workspace, pl);
+    if (pl.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", pl.bytes, workspace_bytes); return NA_ERR_WORKSPACE; }
+    const size_t smem = (size_t)(256 / (D / 8)) * D * sizeof(float);
+    dec::pv_kernel<__half><<<dim3(pl.chunks, n), 256, smem, stream>>>((const __half*)v_fp16, p, pl.partial, N, D, pl.chunks);
+    dec::pv_finish_kernel<<<n, 128, 0, stream>>>(pl.partial, pl.chunks, D, out);
+    NA_LAUNCH_OK("kvread_pv");
+    return NA_OK;
+}
+
+extern "C" int nerfattn_decode_pv(const na_fit_t* models, int32_t n, const float* p, float* out, int32_t precision,
+                                  void* workspace, size_t workspace_bytes, na_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = infer_validate(models, n, true);
+    if (rc) return rc;
+    if (precision != NA_PREC_FP32 && precision != NA_PREC_BF16) { set_error("precision %d not implemented", precision); return NA_ERR_UNSUPPORTED; }
+    if (!p || !out) { set_error("null p / out"); return NA_ERR_INVALID; }
+    if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return NA_ERR_WORKSPACE; }
+    const int D = models[0].D;
+    if (D % 8 || 256 % (D / 8)) { set_error("pv: D/8 must divide 256"); return NA_ERR_UNSUPPORTED; }
+    PvPlan pl; pv_plan(models, n, 0, 0, precision, workspace, pl);
+    if (pl.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", pl.bytes, workspace_bytes); return NA_ERR_WORKSPACE; }
+    const Group& g = pl.g;
+    {   // model table
+        std::vector<FitRec> recs(n);
+        std::vector<float*> outs(n);
+        for (int i = 0; i < n; ++i) {
+            FitRec& r = recs[i];
+            memset(&r, 0, sizeof(r));
+            r.pos = models[i].positions; r.params = models[i].params; r.omega = models[i].omega0;
+            r.mean = models[i].mean; r.stdv = models[i].std;
+            if (!pl.chain) outs[i] = pl.vfull + (size_t)i * g.N * g.D;
+        }
+        NA_CUDA_OK(cudaMemcpyAsync(g.d_recs, recs.data(), n * sizeof(FitRec), cudaMemcpyHostToDevice, stream));
+        if (!pl.chain) NA_CUDA_OK(cudaMemcpyAsync(pl.d_out, outs.data(), n * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    }
+    if (pl.chain) {
+        // V never exists: the forward chain reduces p_t * h_L(t) over the positions, the output layer acts on the sum
+        if ((rc = tc::configure_all()) || (rc = chain::configure_all())) return rc;
+        tc::mirror_weights(g.d_recs, g.lm, n, g.wbf16, stream);
+        NA_LAUNCH_OK("mirror_weights");
+        chain::ChainMaps cm;
+        if ((rc = chain::build_fwd_maps(g.N, g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
+        if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, nullptr, nullptr, stream, p, pl.partial))) return rc;
+        dec::attn_finish_kernel<<<n, 256, g.H * sizeof(float), stream>>>(g.d_recs, pl.partial, g.N / 32, g.H, g.D,
+                                                                         g.lm.w_off[g.L + 1], g.lm.b_off[g.L + 1], out);
+        NA_LAUNCH_OK("attn_finish_kernel");
+        return NA_OK;
+    }
+    // fp32 (and shapes outside the tensor path): reconstruct V in fp32, then the same P.V kernel as the baseline
+    float* act[kMaxHidden + 1];
+    for (int l = 0; l <= g.L; ++l) act[l] = (float*)g.act[l & 1];
+    fp32_forward_hidden(g, act, nullptr, g.L, stream);
+    fp32_output_layer(g, act[g.L], true, stream, pl.d_out, 1);
+    const size_t smem = (size_t)(256 / (D / 8)) * D * sizeof(float);
+    dec::pv_kernel<float><<<dim3(pl.chunks, n), 256, smem, stream>>>(pl.vfull, p, pl.partial, g.N, D, pl.chunks);
+    dec::pv_finish_kernel<<<n, 128, 0, stream>>>(pl.partial, pl.chunks, D, out);
+    NA_LAUNCH_OK("decode_pv");
+    return NA_OK;
+}
+
 extern "C" int nerfattn_debug_gemm_bf16(const void* a_bf16, const void* b_bf16, float* c, int32_t M, int32_t N,
                                         int32_t K, int32_t batch, int32_t a_mn, int32_t b_mn, na_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

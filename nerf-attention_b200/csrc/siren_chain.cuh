@@ -69,6 +69,7 @@ struct ChainArgs {
     __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][128][H]
     float* losspart; int losspart_per_fit; float loss_scale;
     const float* dotvec; float* dotpart;    // forward-only (decode): u [nf][H] fp32, partial scores [nf][CG][N]
+    const float* pvec; float* pvpart;       // forward-only (decode, values): p [nf][N] fp32, partial sums [nf][N/32][H]
     int dbg;                                // NERFATTN_CHAIN_DBG (profiling experiments only)
     int sincos_mode;                        // bit 0: hidden layers, bit 1: layer 0 use the MUFU-core sincos (common.cuh)
 };
@@ -480,6 +481,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
                     uint32_t v[16];
                     float dot = 0.f;
+                    const float prow = (FWD && s == L && g.pvec != nullptr) ? __ldg(g.pvec + (size_t)fit * g.N + row) : 0.f;
                     tmem_ld16(t_row, v);
 #pragma unroll 1
                     for (int u = 0; u < NU; ++u) {
@@ -498,13 +500,17 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc + (u + 1) * 16) + j);
                         }
                         uint32_t so[8], co[8];
+                        float wv[16];
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi) {
                             float a8[8], sn[8], cs[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) a8[j] = arg[gi * 8 + j];
                             if (mufu_hidden) sincos8<true>(a8, sn, cs); else sincos8<false>(a8, sn, cs);
-                            if (FWD && s == L) {                 // decode: u . sin(.) of this row, fp32
+                            if (FWD && s == L && g.pvec != nullptr) {     // decode, values: p_t * sin(.) summed over rows below
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) wv[gi * 8 + j] = prow * sn[j];
+                            } else if (FWD && s == L) {          // decode, keys: u . sin(.) of this row, fp32
                                 const float* uv = g.dotvec + (size_t)fit * H + col0 + u * 16 + gi * 8;
                                 const float4 u0 = __ldg(reinterpret_cast<const float4*>(uv)), u1 = __ldg(reinterpret_cast<const float4*>(uv) + 1);
                                 dot = fmaf(u0.x, sn[0], dot); dot = fmaf(u0.y, sn[1], dot); dot = fmaf(u0.z, sn[2], dot); dot = fmaf(u0.w, sn[3], dot);
@@ -519,9 +525,33 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         if (!(FWD && s == L)) {
                             act_store16(act_u32, r, col0 + u * 16, so);
                             if (!FWD) st_global_256_hint(cdst + u * 16, co, pol_keep);
+                        } else if (g.pvec != nullptr) {
+                            // sum the 16 columns over the 32 rows of this warp: transpose-reduce, 16 shuffles
+                            float w8[8], w4[4], w2[2];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float send = (lane & 16) ? wv[j] : wv[j + 8], keep = (lane & 16) ? wv[j + 8] : wv[j];
+                                w8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float send = (lane & 8) ? w8[j] : w8[j + 4], keep = (lane & 8) ? w8[j + 4] : w8[j];
+                                w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const float send = (lane & 4) ? w4[j] : w4[j + 2], keep = (lane & 4) ? w4[j + 2] : w4[j];
+                                w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                            }
+                            const float send = (lane & 2) ? w2[0] : w2[1], keep = (lane & 2) ? w2[1] : w2[0];
+                            float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                            // lanes 2c and 2c+1 hold column c = (lane >> 1) & 15 of this unit
+                            if (!(lane & 1))
+                                g.pvpart[((size_t)fit * (g.N / 32) + (size_t)mt * 4 + q) * H + col0 + u * 16 + ((lane >> 1) & 15)] = w1;
                         }
                     }
-                    if (FWD && s == L) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
+                    if (FWD && s == L && g.pvec == nullptr) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
                 } else if (s == L + 1) {
                     // ---------------- output layer: dY = 2 (y - t) / (N D), loss partial (siren.py:101)
                     const int ow = D / C::CG;                    // output columns of this thread
@@ -770,11 +800,11 @@ inline int build_fwd_maps(int N, int H, int L, int nf, const LayerMap& lm, __nv_
     return NA_OK;
 }
 inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
-                         const float* u, float* dotpart, cudaStream_t s) {
+                         const float* u, float* dotpart, cudaStream_t s, const float* pvec = nullptr, float* pvpart = nullptr) {
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = N / BM; a.recs = recs;
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
-    a.dotvec = u; a.dotpart = dotpart;
+    a.dotvec = u; a.dotpart = dotpart; a.pvec = pvec; a.pvpart = pvpart;
     a.sincos_mode = sincos_mode();
     return launch(H, cm, a, true, s);
 }

@@ -11,7 +11,7 @@ import ctypes
 import os
 from pathlib import Path
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'bf16': PREC_BF16}
@@ -62,6 +62,13 @@ _SIGNATURES = {
                                      c_void_p]),
     'nerfattn_kvread_qk': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                      c_void_p]),
+    'nerfattn_softmax': (c_int32, [c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    'nerfattn_pv_workspace_bytes': (c_int32, [ctypes.POINTER(NaFit), c_int32, c_int32, c_int32, c_int32,
+                                              ctypes.POINTER(c_size_t)]),
+    'nerfattn_kvread_pv': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_size_t,
+                                     c_void_p]),
+    'nerfattn_decode_pv': (c_int32, [ctypes.POINTER(NaFit), c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                     c_size_t, c_void_p]),
     'nerfattn_debug_gemm_bf16': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_void_p]),
     'nerfattn_debug_sincos': (c_int32, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_void_p]),

@@ -123,6 +123,73 @@ class PackedModels:
         return out
 
 
+    def decode_pv(self, p: torch.Tensor, precision: str = 'bf16', out: torch.Tensor | None = None) -> torch.Tensor:
+        """out [n, D] = sum_t p[i, t] * (SIREN_i(pos_t) * std_i + mean_i) for value models; p fp32 [n, N].
+        In the bf16 mode the values are never materialised (fused forward kernel + one output-layer GEMV)."""
+        lib = _native.lib()
+        prec = _native.precision_code(precision)
+        assert p.dtype == torch.float32 and p.is_contiguous() and p.shape == (self.n, self.seq_len)
+        if out is None:
+            out = torch.empty(self.n, self.d, device=self.device)
+        key = f'nerfattn_pv_workspace_bytes/{prec}'
+        if key not in self._ws:
+            need = ctypes.c_size_t(0)
+            _native.check(lib.nerfattn_pv_workspace_bytes(self.fits, self.n, self.seq_len, self.d, prec,
+                                                          ctypes.byref(need)), key)
+            self._ws[key] = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+        ws = self._ws[key]
+        _native.check(lib.nerfattn_decode_pv(self.fits, self.n, p.data_ptr(), out.data_ptr(), prec, ws.data_ptr(),
+                                             ws.numel(), _native.stream_handle()), 'nerfattn_decode_pv')
+        return out
+
+
+def softmax_(scores: torch.Tensor, scale: float) -> torch.Tensor:
+    """In place: scores[i, :] = softmax(scale * scores[i, :]); scores fp32 [n, N] on the device."""
+    assert scores.dtype == torch.float32 and scores.is_contiguous() and scores.dim() == 2
+    _native.check(_native.lib().nerfattn_softmax(scores.data_ptr(), scores.shape[0], scores.shape[1], float(scale),
+                                                 _native.stream_handle()), 'nerfattn_softmax')
+    return scores
+
+
+_PV_WS: dict = {}
+
+
+def kvread_pv(v_fp16: torch.Tensor, p: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out [n, D] = sum_t p[i, t] V[i, t, :] with V fp16 [n, N, D] streamed from HBM (the decode baseline)."""
+    lib = _native.lib()
+    n, seq, d = v_fp16.shape
+    assert v_fp16.dtype == torch.float16 and v_fp16.is_contiguous() and p.dtype == torch.float32 and p.is_contiguous()
+    if out is None:
+        out = torch.empty(n, d, device=v_fp16.device)
+    key = (n, seq, d, str(v_fp16.device))
+    if key not in _PV_WS:
+        need = ctypes.c_size_t(0)
+        _native.check(lib.nerfattn_pv_workspace_bytes(None, n, seq, d, 0, ctypes.byref(need)), 'nerfattn_pv_workspace_bytes')
+        _PV_WS[key] = torch.empty(max(need.value, 256), dtype=torch.uint8, device=v_fp16.device)
+    ws = _PV_WS[key]
+    _native.check(lib.nerfattn_kvread_pv(v_fp16.data_ptr(), p.data_ptr(), out.data_ptr(), n, seq, d, ws.data_ptr(),
+                                         ws.numel(), _native.stream_handle()), 'nerfattn_kvread_pv')
+    return out
+
+
+def siren_attention(keys: 'PackedModels', values: 'PackedModels', q: torch.Tensor, scale: float | None = None,
+                    precision: str = 'bf16') -> torch.Tensor:
+    """Single-query attention with both caches replaced by their SIRENs (reference README.md:3-8):
+    out [n, D] = softmax(scale * q.K_hat) @ V_hat, neither K_hat nor V_hat materialised in the bf16 mode."""
+    scale = keys.d ** -0.5 if scale is None else scale
+    p = keys.decode_qk(q, precision).clone()
+    softmax_(p, scale)
+    return values.decode_pv(p, precision)
+
+
+def kvread_attention(k_fp16: torch.Tensor, v_fp16: torch.Tensor, q: torch.Tensor, scale: float | None = None) -> torch.Tensor:
+    """The same from an fp16 KV cache in HBM: the latency baseline of siren_attention."""
+    scale = k_fp16.shape[-1] ** -0.5 if scale is None else scale
+    p = kvread_qk(k_fp16, q)
+    softmax_(p, scale)
+    return kvread_pv(v_fp16, p)
+
+
 def kvread_qk(k_fp16: torch.Tensor, q_fp16: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """scores [n, N] = K[n, N, D] . q[n, D] with K streamed from HBM (the decode baseline)."""
     lib = _native.lib()
@@ -291,6 +358,37 @@ def profile_decode(models: list[SIREN], seq_lens: list[int], heads_per_launch: i
             row[f'siren_{prec}_tflops'] = flop * heads_per_launch / t / 1e12
             row[f'siren_{prec}_over_kvread'] = t / t_kv
         table.append(row)
+    return table
+
+
+def profile_attention(models: list[SIREN], seq_lens: list[int], heads_per_launch: int = 64, device: str = 'cuda',
+                      warmup: int = 5, runs: int = 20) -> list[dict]:
+    """Whole single-query attention (q.K, softmax, P.V) per launch of ``heads_per_launch`` heads: from key and
+    value SIRENs (bf16 path, K and V never materialised) vs from an fp16 KV cache streamed out of HBM."""
+    _native.require_cuda(device)
+    table = []
+    for n in seq_lens:
+        batch = [models[i % len(models)] for i in range(heads_per_launch)]
+        keys_m, vals_m = PackedModels(batch, n, device=device), PackedModels(batch[::-1], n, device=device)
+        d = keys_m.d
+        q = torch.randn(heads_per_launch, d, device=device).half()
+        bytes_per_launch = 2 * heads_per_launch * n * d * 2               # K and V, fp16
+        pool = min(max(2, int(512e6 // bytes_per_launch) + 1), 32)
+        kv = [(torch.randn(heads_per_launch, n, d, device=device).half(),
+               torch.randn(heads_per_launch, n, d, device=device).half()) for _ in range(pool)]
+        it = {'i': 0}
+
+        def kv_step():
+            k16, v16 = kv[it['i'] % len(kv)]
+            kvread_attention(k16, v16, q)
+            it['i'] += 1
+        t_kv = _time_cuda(kv_step, warmup, runs)
+        siren_attention(keys_m, vals_m, q, None, 'bf16')
+        t_s = _time_cuda(lambda: siren_attention(keys_m, vals_m, q, None, 'bf16'), warmup, runs)
+        table.append({'seq_len': n, 'heads_per_launch': heads_per_launch, 'kv_bytes_per_launch': bytes_per_launch,
+                      'kvread_attention_us': t_kv * 1e6, 'kvread_gbs': bytes_per_launch / t_kv / 1e9,
+                      'siren_attention_bf16_us': t_s * 1e6, 'siren_over_kvread': t_s / t_kv,
+                      'note': 'siren side includes the per-call model-table upload and bf16 weight mirror'})
     return table
 
 

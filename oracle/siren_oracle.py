@@ -268,3 +268,21 @@ def decode_scores(state: dict[str, torch.Tensor], omega_0: float, mean: torch.Te
 def kvread_scores(k_fp16: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
     """Plain KV-cache attention logits: fp16 keys from memory, fp32 accumulate."""
     return k_fp16.float() @ q.float()
+
+
+def decode_attention(key_state: dict[str, torch.Tensor], value_state: dict[str, torch.Tensor], omega_k: float,
+                     omega_v: float, mean_k: torch.Tensor, std_k: torch.Tensor, mean_v: torch.Tensor,
+                     std_v: torch.Tensor, q: torch.Tensor, seq_len: int, scale: float) -> torch.Tensor:
+    """softmax(scale * q.K_hat) @ V_hat with both caches reconstructed from their SIRENs (the decode
+    the reference describes in README.md:3-8; reconstruction as in evaluate.py:148-152)."""
+    pos = positions_for(seq_len)
+    k_hat = forward(key_state, omega_k, pos) * std_k + mean_k
+    v_hat = forward(value_state, omega_v, pos) * std_v + mean_v
+    p = torch.softmax(scale * (k_hat @ q.float()), dim=0)
+    return p @ v_hat
+
+
+def kvread_attention(k_fp16: torch.Tensor, v_fp16: torch.Tensor, q: torch.Tensor, scale: float) -> torch.Tensor:
+    """Plain single-query attention over an fp16 KV cache, fp32 accumulate."""
+    p = torch.softmax(scale * (k_fp16.float() @ q.float()), dim=0)
+    return p @ v_fp16.float()

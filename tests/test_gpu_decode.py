@@ -121,3 +121,41 @@ def test_scaling_experiment_and_layer_profile_outputs(cuda_device, tmp_path):
                                                           (2, 'key'), (2, 'value')]
     assert json.loads((tmp_path / 'profile' / 'full_layer_profile.json').read_text()) == prof
     assert data['keys'].shape == (2, 256, 128)
+
+
+@pytest.mark.parametrize('name,n', [('medium', 512), ('tiny', 1024), ('large', 256), ('deep', 384)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 5e-5), ('bf16', 3e-2)])
+def test_siren_attention_matches_oracle(cuda_device, name, n, precision, tol):
+    """softmax(scale * q.K_hat) @ V_hat from key and value SIRENs against the CPU restatement."""
+    from nerf_attention.evaluate import siren_attention
+    cfg = next(c for c in na.CONFIGS_FULL if c.name == name)
+    heads = 3
+    ks = [seeded_state(cfg, 128, 170 + i) for i in range(heads)]
+    vs = [seeded_state(cfg, 128, 270 + i) for i in range(heads)]
+    g = torch.Generator().manual_seed(2)
+    mk = [torch.randn(1, 128, generator=g) * 0.1 for _ in range(heads)]
+    sk = [torch.rand(1, 128, generator=g) + 0.5 for _ in range(heads)]
+    mv = [torch.randn(1, 128, generator=g) * 0.1 for _ in range(heads)]
+    sv = [torch.rand(1, 128, generator=g) + 0.5 for _ in range(heads)]
+    q = (torch.randn(heads, 128, generator=g) * 3).half()           # sharp enough that the softmax matters
+    keys = PackedModels([model_from_state(cfg, 128, s) for s in ks], n, mk, sk)
+    values = PackedModels([model_from_state(cfg, 128, s) for s in vs], n, mv, sv)
+    scale = 128 ** -0.5
+    out = siren_attention(keys, values, q.cuda(), scale, precision)
+    again = siren_attention(keys, values, q.cuda(), scale, precision)
+    assert torch.equal(out, again)                                   # deterministic reductions
+    for i in range(heads):
+        ref = orc.decode_attention(ks[i], vs[i], cfg.omega_0, cfg.omega_0, mk[i], sk[i], mv[i], sv[i], q[i], n, scale)
+        assert rel_err(out[i].cpu(), ref) <= tol, i
+
+
+@pytest.mark.parametrize('n,heads,d', [(512, 3, 128), (2048, 8, 128), (300, 2, 64), (5, 1, 256)])
+def test_kvread_attention_matches_torch(cuda_device, n, heads, d):
+    from nerf_attention.evaluate import kvread_attention
+    g = torch.Generator(device='cuda').manual_seed(n)
+    k = torch.randn(heads, n, d, device='cuda', generator=g).half()
+    v = torch.randn(heads, n, d, device='cuda', generator=g).half()
+    q = torch.randn(heads, d, device='cuda', generator=g).half()
+    out = kvread_attention(k, v, q)
+    ref = torch.stack([orc.kvread_attention(k[i].cpu(), v[i].cpu(), q[i].cpu(), d ** -0.5) for i in range(heads)])
+    assert rel_err(out.cpu(), ref) <= 2e-5
