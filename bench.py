@@ -371,7 +371,7 @@ def run_native(args) -> None:
                 'frac': k_ach / peaks['bf16_sustained'],
                 'traffic': (traffic or {}).get('chain_dram_bytes_per_epoch'),
                 'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernels timed inside a seconds-long step)",
-                'kernel': 'chain::chain_kernel<H,NS,false> (fused forward + loss + dX per 128-row tile; one launch per '
+                'kernel': 'chain::chain_kernel<H,NS,0,CL> (fused forward + loss + dX per 128-row tile; one launch per '
                           'shape group and epoch, 5 per epoch): algorithmic FLOPs 4N(LH^2+HD)+2NH per fit-epoch, all 280 '
                           'fits / summed device time of the 5 launches of one epoch (NERFATTN_PHASE=1 minus =8, CUDA events)',
                 'per_launch': 'one epoch = 5 chain launches; achieved/traffic are per epoch (sum over the 5)',

@@ -191,9 +191,12 @@ __device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], floa
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the pair (2c, 2c+1) takes adjacent row tiles of one fit, each
 // CTA issues half of every weight stage's 64 x 64 boxes as a multicast to both, so the L2 -> SM weight
 // traffic and the time to fill a stage halve; nothing else is shared (each CTA issues its own MMAs).
-template <int H, int NS, bool FWD, int CL>
+// MODE 0: training chain; 1: forward only, u . sin(.) per position (decode logits); 2: forward only,
+// p_t * sin(.) summed over the positions (decode, values)
+template <int H, int NS, int MODE, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
+    constexpr bool FWD = MODE != 0;
     using C = Cfg<H, NS>;
     constexpr int NSLOT = C::NSLOT;
     constexpr int STAGES = C::STAGES;
@@ -481,7 +484,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
                     uint32_t v[16];
                     float dot = 0.f;
-                    const float prow = (FWD && s == L && g.pvec != nullptr) ? __ldg(g.pvec + (size_t)fit * g.N + row) : 0.f;
+                    const float prow = (MODE == 2 && s == L) ? __ldg(g.pvec + (size_t)fit * g.N + row) : 0.f;
                     tmem_ld16(t_row, v);
 #pragma unroll 1
                     for (int u = 0; u < NU; ++u) {
@@ -507,10 +510,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) a8[j] = arg[gi * 8 + j];
                             if (mufu_hidden) sincos8<true>(a8, sn, cs); else sincos8<false>(a8, sn, cs);
-                            if (FWD && s == L && g.pvec != nullptr) {     // decode, values: p_t * sin(.) summed over rows below
+                            if (MODE == 2 && s == L) {     // decode, values: p_t * sin(.) summed over rows below
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) wv[gi * 8 + j] = prow * sn[j];
-                            } else if (FWD && s == L) {          // decode, keys: u . sin(.) of this row, fp32
+                            } else if (MODE == 1 && s == L) {          // decode, keys: u . sin(.) of this row, fp32
                                 const float* uv = g.dotvec + (size_t)fit * H + col0 + u * 16 + gi * 8;
                                 const float4 u0 = __ldg(reinterpret_cast<const float4*>(uv)), u1 = __ldg(reinterpret_cast<const float4*>(uv) + 1);
                                 dot = fmaf(u0.x, sn[0], dot); dot = fmaf(u0.y, sn[1], dot); dot = fmaf(u0.z, sn[2], dot); dot = fmaf(u0.w, sn[3], dot);
@@ -525,7 +528,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         if (!(FWD && s == L)) {
                             act_store16(act_u32, r, col0 + u * 16, so);
                             if (!FWD) st_global_256_hint(cdst + u * 16, co, pol_keep);
-                        } else if (g.pvec != nullptr) {
+                        } else if (MODE == 2) {
                             // sum the 16 columns over the 32 rows of this warp: transpose-reduce, 16 shuffles
                             float w8[8], w4[4], w2[2];
 #pragma unroll
@@ -551,7 +554,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                                 g.pvpart[((size_t)fit * (g.N / 32) + (size_t)mt * 4 + q) * H + col0 + u * 16 + ((lane >> 1) & 15)] = w1;
                         }
                     }
-                    if (FWD && s == L && g.pvec == nullptr) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
+                    if (MODE == 1 && s == L) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
                 } else if (s == L + 1) {
                     // ---------------- output layer: dY = 2 (y - t) / (N D), loss partial (siren.py:101)
                     const int ow = D / C::CG;                    // output columns of this thread
@@ -686,7 +689,7 @@ inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __
     return NA_OK;
 }
 
-template <int H, int NS, bool FWD, int CL>
+template <int H, int NS, int MODE, int CL>
 inline cudaError_t launch_one(int grid, const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS);
@@ -695,33 +698,36 @@ inline cudaError_t launch_one(int grid, const ChainMaps& maps, const ChainArgs& 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, chain_kernel<H, NS, FWD, CL>, maps, a);
+    return cudaLaunchKernelEx(&cfg, chain_kernel<H, NS, MODE, CL>, maps, a);
 }
+template <int H, int NS>
+inline cudaError_t launch_mode(int mode, int grid, const ChainMaps& maps, const ChainArgs& a, cudaStream_t s) {
+    return mode == 0 ? launch_one<H, NS, 0, 1>(grid, maps, a, s)
+         : mode == 1 ? launch_one<H, NS, 1, 1>(grid, maps, a, s) : launch_one<H, NS, 2, 1>(grid, maps, a, s);
+}
+// mode: 0 training, 1 decode logits, 2 decode values.  The 2-CTA cluster variant exists for training only.
 template <int H>
-inline int launch_h(const ChainMaps& maps, const ChainArgs& a, bool fwd, cudaStream_t s) {
+inline int launch_h(const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s) {
     const int tiles = a.nf * a.mtiles;
-    const bool cl = use_cluster(a.N);
+    const bool cl = mode == 0 && use_cluster(a.N);
     int grid = std::min(tiles, num_sms());
     if (cl) grid &= ~1;
     cudaError_t e;
     constexpr int NSD = (H <= 256) ? 2 : 1;                  // default slots
-    if (cl && slots_for(H) == NSD) {
-        e = fwd ? launch_one<H, NSD, true, 2>(grid, maps, a, s) : launch_one<H, NSD, false, 2>(grid, maps, a, s);
-    } else if constexpr (H <= 256) {
-        if (slots_for(H) == 2) e = fwd ? launch_one<H, 2, true, 1>(grid, maps, a, s) : launch_one<H, 2, false, 1>(grid, maps, a, s);
-        else e = fwd ? launch_one<H, 1, true, 1>(grid, maps, a, s) : launch_one<H, 1, false, 1>(grid, maps, a, s);
-    } else {
-        e = fwd ? launch_one<H, 1, true, 1>(grid, maps, a, s) : launch_one<H, 1, false, 1>(grid, maps, a, s);
-    }
+    if (cl && slots_for(H) == NSD) e = launch_one<H, NSD, 0, 2>(grid, maps, a, s);
+    else if constexpr (H <= 256) {
+        if (slots_for(H) == 2) e = launch_mode<H, 2>(mode, grid, maps, a, s);
+        else e = launch_mode<H, 1>(mode, grid, maps, a, s);
+    } else e = launch_mode<H, 1>(mode, grid, maps, a, s);
     if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
 }
-inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, bool fwd, cudaStream_t s) {
+inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s) {
     switch (H) {
-        case 64: return launch_h<64>(maps, a, fwd, s);
-        case 128: return launch_h<128>(maps, a, fwd, s);
-        case 256: return launch_h<256>(maps, a, fwd, s);
-        case 512: return launch_h<512>(maps, a, fwd, s);
+        case 64: return launch_h<64>(maps, a, mode, s);
+        case 128: return launch_h<128>(maps, a, mode, s);
+        case 256: return launch_h<256>(maps, a, mode, s);
+        case 512: return launch_h<512>(maps, a, mode, s);
         default: set_error("chain: unsupported H %d", H); return NA_ERR_UNSUPPORTED;
     }
 }
@@ -766,7 +772,7 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
     a.sincos_mode = sincos_mode();
     { const char* e = getenv("NERFATTN_CHAIN_DBG"); a.dbg = e ? atoi(e) : 0; }
     const int phases = phase_mask();
-    if ((phases & 1) && (rc = launch(H, cm, a, false, s))) return rc;
+    if ((phases & 1) && (rc = launch(H, cm, a, 0, s))) return rc;
     if (!(phases & 2)) return NA_OK;
     TcArgs base{};
     base.nb = nf; base.recs = recs;
@@ -792,11 +798,10 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).
 inline int decode_parts(int H) { return slots_for(H) == 2 ? 2 : 4; }
-inline int build_fwd_maps(int N, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
+inline int build_fwd_maps(int /*N*/, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
     int rc;
     for (int l = 1; l <= L; ++l)
-        if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], H, H, nf, lm.P, false,
-                                   use_cluster(N) ? 64 : H >= 256 ? 256 : H))) return rc;
+        if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], H, H, nf, lm.P, false, H >= 256 ? 256 : H))) return rc;
     return NA_OK;
 }
 inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
@@ -806,7 +811,7 @@ inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm,
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
     a.dotvec = u; a.dotpart = dotpart; a.pvec = pvec; a.pvpart = pvpart;
     a.sincos_mode = sincos_mode();
-    return launch(H, cm, a, true, s);
+    return launch(H, cm, a, pvec ? 2 : 1, s);
 }
 
 inline int configure_all() {
@@ -814,12 +819,13 @@ inline int configure_all() {
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
         auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
-#define NA_CHAIN_CFG(HH, NS, CL) \
-        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM)); \
-        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, true, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM));
-        NA_CHAIN_CFG(64, 2, 1) NA_CHAIN_CFG(128, 2, 1) NA_CHAIN_CFG(256, 2, 1)
-        NA_CHAIN_CFG(64, 1, 1) NA_CHAIN_CFG(128, 1, 1) NA_CHAIN_CFG(256, 1, 1) NA_CHAIN_CFG(512, 1, 1)
-        NA_CHAIN_CFG(64, 2, 2) NA_CHAIN_CFG(128, 2, 2) NA_CHAIN_CFG(256, 2, 2) NA_CHAIN_CFG(512, 1, 2)
+#define NA_CHAIN_CFG1(HH, NS, MODE, CL) \
+        acc(cudaFuncSetAttribute(chain_kernel<HH, NS, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM));
+#define NA_CHAIN_CFG(HH, NS) NA_CHAIN_CFG1(HH, NS, 0, 1) NA_CHAIN_CFG1(HH, NS, 1, 1) NA_CHAIN_CFG1(HH, NS, 2, 1)
+        NA_CHAIN_CFG(64, 2) NA_CHAIN_CFG(128, 2) NA_CHAIN_CFG(256, 2)
+        NA_CHAIN_CFG(64, 1) NA_CHAIN_CFG(128, 1) NA_CHAIN_CFG(256, 1) NA_CHAIN_CFG(512, 1)
+        NA_CHAIN_CFG1(64, 2, 0, 2) NA_CHAIN_CFG1(128, 2, 0, 2) NA_CHAIN_CFG1(256, 2, 0, 2) NA_CHAIN_CFG1(512, 1, 0, 2)
+#undef NA_CHAIN_CFG1
 #undef NA_CHAIN_CFG
     });
     if (err != cudaSuccess) { set_error("cudaFuncSetAttribute(chain smem) failed: %s", cudaGetErrorString(err)); return NA_ERR_CUDA; }
