@@ -40,7 +40,6 @@ constexpr int NEPI = 16;                          // epilogue warps 4..19
 constexpr int NTHREADS = (NCTRL + NEPI) * 32;     // 640
 constexpr int CHUNK_BYTES = BM * 64 * 2;          // one K-chunk of an A operand: 128 rows x 64 bf16
 constexpr int STAGE_BYTES = 256 * 64 * 2;         // one K-chunk of a weight operand: <= 256 x 64 bf16
-constexpr bool kClusterDefault = false;           // tuned on B200, see profiles/README.md
 constexpr int SMEM_BUDGET = 227 * 1024 - 512;     // dynamic shared memory per CTA, minus the barrier block
 
 // NS = tiles in flight per CTA (2 needs 2 x max(H, 256) accumulator columns and operand buffers)
@@ -126,16 +125,38 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-// 2-CTA cluster: one L2 read feeds the same ring stage of both CTAs (they work on adjacent row tiles of
-// the same fit, i.e. the same weights), and a stage is released to the loaders by both MMA warps.
-__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+// cta_group::2: one MMA spans the CTA pair (M = 256: 128 rows of A and D in each CTA, B split in halves between
+// the two shared memories), issued by the leader CTA only
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+// TMA load of the peer CTA's half of a weight stage: lands in the issuing CTA's shared memory, completes the
+// transaction count of the LEADER's barrier (the MMA that consumes both halves is issued there)
+__device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t cta_rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(cta_rank));
+    return ra;
+}
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* local_bar, uint32_t cta_rank) {     // arrive on `cta_rank`'s copy
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_bar)), "r"(cta_rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -199,20 +220,23 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     constexpr bool FWD = MODE != 0;
     using C = Cfg<H, NS>;
     constexpr int NSLOT = C::NSLOT;
-    constexpr int STAGES = C::STAGES;
+    // CTA pair: each CTA holds half of every weight stage -> twice as many stages of half the size in the same ring
+    constexpr int STAGES = (CL == 2) ? 2 * C::STAGES : C::STAGES;
+    constexpr int STAGE_SZ = (CL == 2) ? STAGE_BYTES / 2 : STAGE_BYTES;
     const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
     // tile of (round, slot): clusters stride over tile pairs, CTAs of a cluster take consecutive tiles
     const int cl_stride = (int)gridDim.x / CL;
     auto tile_of = [&](int round, int slot) { return CL * ((int)blockIdx.x / CL + (round * NSLOT + slot) * cl_stride) + (int)crank; };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_ring = smem + NSLOT * C::ACT_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + STAGES * STAGE_SZ);
     uint64_t* full = bars;                       // [STAGES]  weights landed
     uint64_t* empty = bars + STAGES;             // [STAGES]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * STAGES;      // [2]       accumulator of the slot complete
     uint64_t* act_ready = bars + 2 * STAGES + 2; // [2]       A operand of the slot written, accumulator drained
     uint64_t* buf_free = bars + 2 * STAGES + 4;  // [2]       the TMA store of the slot's operand buffer has read it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    uint64_t* mma_ready = bars + 2 * STAGES + 6; // [2]       CL = 2, leader: the operand buffers of both CTAs are written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = g.L, D = g.D;
@@ -221,13 +245,21 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) { printf("nerfattn: chain smem base not 1024-aligned\n"); __trap(); }
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], C::EPW); mbar_init(&buf_free[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1); mbar_init(&act_ready[i], C::EPW); mbar_init(&buf_free[i], 1);
+            mbar_init(&mma_ready[i], 2 * C::EPW);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CL == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -251,9 +283,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 for (int np = 0; np < st.nparts; ++np)
                     for (int kc = 0; kc < st.kch; ++kc) {
                         if (CL == 2) {
-                            for (int i = (int)crank; i < st.n / 64; i += 2) {
-                                if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256 + i * 64, fit);
-                                else tma_prefetch_3d(map, np * 256 + i * 64, kc * 64, fit);
+                            const int nb = st.n / 128, b0 = (int)crank * nb;
+                            for (int j = 0; j < nb; ++j) {
+                                if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256 + (b0 + j) * 64, fit);
+                                else tma_prefetch_3d(map, np * 256 + (b0 + j) * 64, kc * 64, fit);
                             }
                         } else if (!st.mn) tma_prefetch_3d(map, kc * 64, np * 256, fit);
                         else
@@ -277,7 +310,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 for (int s = 1; s < nsteps; ++s) {
                     const Step st = step_info<H>(s, L, D);
                     const CUtensorMap* map = st.mn ? &maps.wmn[st.layer] : &maps.wk[st.layer];
-                    const uint32_t tx = (uint32_t)st.n * 128u;
+                    const uint32_t tx = (uint32_t)st.n * 128u;           // both halves land on the leader's barrier when CL == 2
                     for (int slot = 0; slot < NSLOT; ++slot) {
                         const int tile = tile_of(round, slot);
                         if (tile >= total_tiles) break;
@@ -293,13 +326,17 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         for (int np = 0; np < st.nparts; ++np)
                             for (int kc = 0; kc < st.kch; ++kc) {
                                 mbar_wait(&empty[stage], phase ^ 1);
-                                mbar_expect_tx(&full[stage], tx);
-                                uint8_t* sb = smem_ring + stage * STAGE_BYTES;
+                                if (CL == 1 || crank == 0) mbar_expect_tx(&full[stage], tx);
+                                uint8_t* sb = smem_ring + stage * STAGE_SZ;
                                 if (CL == 2) {
-                                    // 64 x 64 boxes (the same map serves K-major and MN-major use); this CTA issues every other one
-                                    for (int i = (int)crank; i < st.n / 64; i += 2) {
-                                        if (!st.mn) tma_load_3d_mc(sb + i * 8192, map, &full[stage], kc * 64, np * 256 + i * 64, fit, 3);
-                                        else tma_load_3d_mc(sb + i * 8192, map, &full[stage], np * 256 + i * 64, kc * 64, fit, 3);
+                                    // this CTA's half of B (n/2 rows K-major, or n/2 columns MN-major) as 64 x 64 boxes
+                                    const int nb = st.n / 128, b0 = (int)crank * nb;
+                                    const uint32_t lbar = mapa_u32(&full[stage], 0);
+                                    for (int j = 0; j < nb; ++j) {
+                                        const int c0 = st.mn ? np * 256 + (b0 + j) * 64 : kc * 64;
+                                        const int c1 = st.mn ? kc * 64 : np * 256 + (b0 + j) * 64;
+                                        if (crank == 0) tma_load_3d(sb + j * 8192, map, &full[stage], c0, c1, fit);
+                                        else tma_load_3d_2cta(sb + j * 8192, map, lbar, c0, c1, fit);
                                     }
                                 } else if (!st.mn) tma_load_3d(sb, map, &full[stage], kc * 64, np * 256, fit);
                                 else
@@ -316,25 +353,29 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         // Step s contracts what the epilogue wrote in step s-1 (warp 2 stores the same buffer to global
         // meanwhile).  Step `nsteps` has no MMA: it only acknowledges the phase (see below).
         int stage = 0; uint32_t phase = 0;
-        uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot]
+        uint32_t rdy_phase = 0;                       // bit `slot` = parity of act_ready[slot] / mma_ready[slot]
         for (int round = 0;; ++round) {
             if (tile_of(round, 0) >= total_tiles) break;
             for (int s = 1; s <= (FWD ? nsteps - 1 : nsteps); ++s) {
                 const Step st = step_info<H>(s < nsteps ? s : 1, L, D);
-                const uint32_t idesc = make_idesc(st.n, false, st.mn != 0);
+                const uint32_t idesc = (CL == 2) ? make_idesc_m(256, st.n, st.mn != 0) : make_idesc(st.n, false, st.mn != 0);
                 const uint32_t b_lbo = st.mn ? 8192u : 0u;
                 const uint32_t b_kadv = st.mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
                 for (int slot = 0; slot < NSLOT; ++slot) {
                     const int tile = tile_of(round, slot);
                     if (tile >= total_tiles) break;
-                    mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
+                    if (CL == 2 && crank != 0) continue;         // peer CTA: the leader issues the pair's MMAs
+                    mbar_wait(CL == 2 ? &mma_ready[slot] : &act_ready[slot], (rdy_phase >> slot) & 1u);
                     rdy_phase ^= 1u << slot;
                     tc_fence_after();
                     uint8_t* const act = smem + slot * C::ACT_BYTES;
                     if (s == nsteps) {
                         // No MMA: acknowledge the phase.  The next tile's E0 waits for this, otherwise a fast slot could
                         // complete act_ready twice before this warp looked at it (parity waits alias after two phases).
-                        if (lane == 0) mbar_arrive(&acc_full[slot]);
+                        if (lane == 0) {
+                            mbar_arrive(&acc_full[slot]);
+                            if (CL == 2) mbar_arrive_cluster(&acc_full[slot], 1);
+                        }
                         __syncwarp();
                         continue;
                     }
@@ -346,13 +387,23 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             tc_fence_after();
                             if (lane == 0) {
                                 const uint64_t adesc0 = make_desc(act_u32 + kc * CHUNK_BYTES, 0, 1024);
-                                const uint64_t bdesc0 = make_desc(smem_u32(smem_ring + stage * STAGE_BYTES), b_lbo, 1024);
+                                const uint64_t bdesc0 = make_desc(smem_u32(smem_ring + stage * STAGE_SZ), b_lbo, 1024);
+                                const bool last = np == st.nparts - 1 && kc == st.kch - 1;
+                                if (CL == 2) {
 #pragma unroll
-                                for (int k = 0; k < 64 / UMMA_K; ++k)
-                                    tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
-                                                (kc > 0 || k > 0) ? 1u : 0u);
-                                if (CL == 2) tc_commit_mc(&empty[stage], 3); else tc_commit(&empty[stage]);
-                                if (np == st.nparts - 1 && kc == st.kch - 1) tc_commit(&acc_full[slot]);
+                                    for (int k = 0; k < 64 / UMMA_K; ++k)
+                                        tc_mma_bf16_2cta(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
+                                                         (kc > 0 || k > 0) ? 1u : 0u);
+                                    tc_commit_2cta(&empty[stage], 3);
+                                    if (last) tc_commit_2cta(&acc_full[slot], 3);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 64 / UMMA_K; ++k)
+                                        tc_mma_bf16(d_tmem, adesc0 + (uint64_t)(k * 2), bdesc0 + (uint64_t)(k * b_kadv), idesc,
+                                                    (kc > 0 || k > 0) ? 1u : 0u);
+                                    tc_commit(&empty[stage]);
+                                    if (last) tc_commit(&acc_full[slot]);
+                                }
                             }
                             __syncwarp();
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -636,7 +687,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&act_ready[slot]);
+                if (lane == 0) {
+                    mbar_arrive(&act_ready[slot]);
+                    if (CL == 2) mbar_arrive_cluster(&mma_ready[slot], 0);     // the pair's MMA is issued by the leader CTA
+                }
             }
         }
 #ifdef NA_CHAIN_TIMING
@@ -650,8 +704,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     __syncthreads();
     if (CL == 2) cluster_sync_all();              // the peer may still multicast into / arrive on this CTA's shared memory
     tc_fence_after();
-    if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (warp == 1) {
+        if (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------ host
@@ -660,11 +716,14 @@ inline int slots_for(int H) {
     const char* e = getenv("NERFATTN_CHAIN_SLOTS");
     return (H <= 256 && !(e && atoi(e) == 1)) ? 2 : 1;
 }
-// NERFATTN_CLUSTER=0 disables the 2-CTA cluster (multicast weight loads); it needs an even number of row tiles
-// per fit so that a pair never straddles two fits
-inline bool use_cluster(int N) {
+// NERFATTN_CLUSTER=1 enables the CTA-pair variant (cta_group::2 MMAs, each CTA loads half of every weight stage); it
+// needs an even number of row tiles per fit so that a pair never straddles two fits
+inline bool use_cluster(int N, int H = 256, int D = 128) {
+    if (H < 128 || D < 128) return false;             // each CTA of the pair holds >= 64 rows / columns of every B operand
+    // default: pair mode for H = 512 (one slot, 512 KB of weights per step: halving the per-SM weight stream gains
+    // ~9 %); for H <= 256 the two-slot kernel is as fast without the pair's lock-step (measured, profiles/README.md)
     const char* e = getenv("NERFATTN_CLUSTER");
-    const bool on = e ? atoi(e) != 0 : kClusterDefault;
+    const bool on = e ? atoi(e) != 0 : H >= 512;
     const char* sl = getenv("NERFATTN_CHAIN_SLOTS");
     return on && !(sl && atoi(sl) == 1) && (N / BM) % 2 == 0 && num_sms() % 2 == 0;
 }
@@ -682,7 +741,7 @@ inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __
     if ((rc = make_operand_map(&m.yout, dy, N, D, nf, (size_t)N * D, false, BM))) return rc;
     for (int l = 1; l <= L + 1; ++l) {
         const int rows = lm.out_dim[l];
-        const int box = use_cluster(N) ? 64 : (l == L + 1) ? D : (H >= 256 ? 256 : H);
+        const int box = use_cluster(N, H, D) ? 64 : (l == L + 1) ? D : (H >= 256 ? 256 : H);
         if ((rc = make_operand_map(&m.wk[l], wbf16 + lm.w_off[l], rows, H, nf, lm.P, false, box))) return rc;
         if ((rc = make_operand_map(&m.wmn[l], wbf16 + lm.w_off[l], rows, H, nf, lm.P, true, 0))) return rc;
     }
@@ -709,7 +768,7 @@ inline cudaError_t launch_mode(int mode, int grid, const ChainMaps& maps, const 
 template <int H>
 inline int launch_h(const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s) {
     const int tiles = a.nf * a.mtiles;
-    const bool cl = mode == 0 && use_cluster(a.N);
+    const bool cl = mode == 0 && use_cluster(a.N, H, a.D);
     int grid = std::min(tiles, num_sms());
     if (cl) grid &= ~1;
     cudaError_t e;

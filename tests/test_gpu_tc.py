@@ -173,7 +173,7 @@ def test_chain_kernel_agrees_with_unfused_path(cuda_device, monkeypatch, h, l, w
     kv = smooth_tensor(5, n, d)
 
     def run(epochs, **env):
-        for k in ('NERFATTN_NO_CHAIN', 'NERFATTN_CHAIN_SLOTS', 'NERFATTN_SINCOS'):
+        for k in ('NERFATTN_NO_CHAIN', 'NERFATTN_CHAIN_SLOTS', 'NERFATTN_SINCOS', 'NERFATTN_CLUSTER'):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -181,7 +181,7 @@ def test_chain_kernel_agrees_with_unfused_path(cuda_device, monkeypatch, h, l, w
 
     ref1 = run(1, NERFATTN_NO_CHAIN='1')
     g_ref = ref1.model.adam_state[0].cpu()
-    variants = [{}, {'NERFATTN_CHAIN_SLOTS': '1'}, {'NERFATTN_SINCOS': '0'}]
+    variants = [{}, {"NERFATTN_CHAIN_SLOTS": "1"}, {"NERFATTN_SINCOS": "0"}, {"NERFATTN_CLUSTER": "1"}, {"NERFATTN_CLUSTER": "0"}]
     for env in variants:
         got = run(1, **env)
         assert got.losses[0] == pytest.approx(ref1.losses[0], rel=1e-3), env
