@@ -90,9 +90,10 @@ static int validate(const na_fit_t* fits, int nfits, int precision) {
         if (f.N < 2 || f.D < 1 || f.H < 1 || f.L < 0) { set_error("fit %d: bad shape", i); return NA_ERR_INVALID; }
         if (f.L > kMaxHidden) { set_error("fit %d: hidden_layers %d > %d", i, f.L, kMaxHidden); return NA_ERR_UNSUPPORTED; }
         if (f.H % 8 || f.D % 4) { set_error("fit %d: H must be a multiple of 8 and D a multiple of 4", i); return NA_ERR_UNSUPPORTED; }
-        if (precision == NA_PREC_BF16 && !tc::shape_supported(f.N, f.D, f.H, f.L)) {
-            set_error("fit %d: bf16 path needs N %% 128 == 0, H in {64,128,256,512}, D %% 64 == 0 and D <= 256 "
-                      "(got N=%d D=%d H=%d)", i, f.N, f.D, f.H);
+        if (precision == NA_PREC_BF16 && !tc::shape_supported(f.N, f.D, f.H, f.L) &&
+            !(chain_enabled() && chain::shape_supported(f.N, f.D, f.H, f.L))) {
+            set_error("fit %d: bf16 path needs H in {64,128,256,512}, D in {64,128,256} and hidden_layers >= 1 "
+                      "(any N), or N %% 128 == 0 without hidden layers (got N=%d D=%d H=%d L=%d)", i, f.N, f.D, f.H, f.L);
             return NA_ERR_UNSUPPORTED;
         }
         if (!f.positions || !f.targets || !f.params) { set_error("fit %d: null pointer", i); return NA_ERR_INVALID; }
@@ -738,8 +739,9 @@ extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void*
     if (!q_fp16 || !scores) { set_error("null q / scores"); return NA_ERR_INVALID; }
     if (!workspace || ((uintptr_t)workspace & 255)) { set_error("workspace must be a 256-byte aligned device pointer"); return NA_ERR_WORKSPACE; }
     const bool bf = precision == NA_PREC_BF16;
-    if (bf && (!tc::shape_supported(models[0].N, 128, models[0].H, models[0].L))) {
-        set_error("bf16 decode needs N %% 128 == 0 and H in {64,128,256,512}"); return NA_ERR_UNSUPPORTED;
+    if (bf && !tc::shape_supported(models[0].N, 128, models[0].H, models[0].L) &&
+        !(chain_enabled() && chain::shape_supported(models[0].N, 128, models[0].H, models[0].L))) {
+        set_error("bf16 decode needs H in {64,128,256,512} and hidden_layers >= 1 (any N), or N %% 128 == 0"); return NA_ERR_UNSUPPORTED;
     }
     InferPlan p; infer_plan(models, n, precision, true, workspace, p);
     if (p.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", p.bytes, workspace_bytes); return NA_ERR_WORKSPACE; }
@@ -855,7 +857,7 @@ static void pv_plan(const na_fit_t* m, int n, int N, int D, int precision, void*
     p.chain = precision == NA_PREC_BF16 && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
     if (p.chain) {
         g.wbf16 = ar.take<__nv_bfloat16>((size_t)n * g.lm.P);
-        p.partial = ar.take<float>((size_t)n * (g.N / 32) * g.H);
+        p.partial = ar.take<float>((size_t)n * (g.mtiles * 4) * g.H);
     } else {
         const size_t nh = (size_t)n * g.N * g.H;
         g.act[0] = ar.take<char>(nh * 4);
@@ -938,7 +940,7 @@ extern "C" int nerfattn_decode_pv(const na_fit_t* models, int32_t n, const float
         chain::ChainMaps cm;
         if ((rc = chain::build_fwd_maps(g.N, g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
         if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, nullptr, nullptr, stream, p, pl.partial))) return rc;
-        dec::attn_finish_kernel<<<n, 256, g.H * sizeof(float), stream>>>(g.d_recs, pl.partial, g.N / 32, g.H, g.D,
+        dec::attn_finish_kernel<<<n, 256, g.H * sizeof(float), stream>>>(g.d_recs, pl.partial, g.mtiles * 4, g.H, g.D,
                                                                          g.lm.w_off[g.L + 1], g.lm.b_off[g.L + 1], out);
         NA_LAUNCH_OK("attn_finish_kernel");
         return NA_OK;

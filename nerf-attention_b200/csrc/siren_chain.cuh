@@ -79,11 +79,13 @@ struct ChainMaps {
     CUtensorMap hout[kMaxHidden + 1]; CUtensorMap zout[kMaxHidden + 1]; CUtensorMap yout;
 };
 
+// Any sequence length: the last row tile may be ragged (rows >= N are masked out of the loss, produce dY = 0 and
+// hence no gradient, and are clipped by the TMA stores / zero-filled by the dW kernel's TMA loads).
 inline bool shape_supported(int N, int D, int H, int L) {
-    return tc::shape_supported(N, D, H, L) && L >= 1;
+    return N >= 1 && (H == 64 || H == 128 || H == 256 || H == 512) && (D == 64 || D == 128 || D == 256) && L >= 1;
 }
 inline int slots_for(int H);
-inline int loss_partials_per_fit(int N, int H) { return (N / BM) * (NEPI / slots_for(H)); }   // one per epilogue warp of the tile
+inline int loss_partials_per_fit(int N, int H) { return ceil_div(N, BM) * (NEPI / slots_for(H)); }   // one per epilogue warp of the tile
 
 __device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -478,6 +480,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
             const FitRec* rec = &g.recs[fit];
             const int row = mt * BM + r;
+            const bool row_ok = row < g.N;                 // ragged last tile
+            const int row_c = row_ok ? row : g.N - 1;      // a valid row to read inputs from
             const float omega = rec->omega;
             for (int s = 0; s < nsteps; ++s) {
 #ifdef NA_CHAIN_TIMING
@@ -492,7 +496,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         NA_T1();
                     }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
-                    const float x = __ldg(rec->pos + row);
+                    const float x = __ldg(rec->pos + row_c);
                     const float* w0 = rec->params + g.w_off[0] + col0;
                     const float* b0 = rec->params + g.b_off[0] + col0;
                     float4 wn[2], bn[2];                         // weights / biases of the next 8 columns
@@ -535,7 +539,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
                     uint32_t v[16];
                     float dot = 0.f;
-                    const float prow = (MODE == 2 && s == L) ? __ldg(g.pvec + (size_t)fit * g.N + row) : 0.f;
+                    const float prow = (MODE == 2 && s == L && row_ok) ? __ldg(g.pvec + (size_t)fit * g.N + row) : 0.f;
                     tmem_ld16(t_row, v);
 #pragma unroll 1
                     for (int u = 0; u < NU; ++u) {
@@ -602,16 +606,17 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
                             // lanes 2c and 2c+1 hold column c = (lane >> 1) & 15 of this unit
                             if (!(lane & 1))
-                                g.pvpart[((size_t)fit * (g.N / 32) + (size_t)mt * 4 + q) * H + col0 + u * 16 + ((lane >> 1) & 15)] = w1;
+                                g.pvpart[((size_t)fit * (g.mtiles * 4) + (size_t)mt * 4 + q) * H + col0 + u * 16 + ((lane >> 1) & 15)] = w1;
                         }
                     }
-                    if (MODE == 1 && s == L) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
+                    if (MODE == 1 && s == L && row_ok) g.dotpart[((size_t)fit * C::CG + cg) * g.N + row] = dot;
                 } else if (s == L + 1) {
                     // ---------------- output layer: dY = 2 (y - t) / (N D), loss partial (siren.py:101)
                     const int ow = D / C::CG;                    // output columns of this thread
                     const int ocol0 = cg * ow;
                     const float* bsrc = rec->params + g.b_off[L + 1] + ocol0;
-                    const float* tn = rec->tnorm + (size_t)row * D + ocol0;
+                    const float* tn = rec->tnorm + (size_t)row_c * D + ocol0;
+                    const float rmask = row_ok ? 1.f : 0.f;      // rows past the sequence: no loss, dY = 0, no gradient
                     const int nuo = ow / 16;
                     uint32_t ta[16], tb[16];                     // targets of this unit and the next: two units in flight
                     ld_global_nc_na_256(tn, &ta[0]); ld_global_nc_na_256(tn + 8, &ta[8]);
@@ -630,10 +635,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(bsrc + u * 16 + j));
-                            const float e0 = (__uint_as_float(v[j + 0]) + bb.x) - __uint_as_float(tt[j + 0]);
-                            const float e1 = (__uint_as_float(v[j + 1]) + bb.y) - __uint_as_float(tt[j + 1]);
-                            const float e2 = (__uint_as_float(v[j + 2]) + bb.z) - __uint_as_float(tt[j + 2]);
-                            const float e3 = (__uint_as_float(v[j + 3]) + bb.w) - __uint_as_float(tt[j + 3]);
+                            const float e0 = rmask * ((__uint_as_float(v[j + 0]) + bb.x) - __uint_as_float(tt[j + 0]));
+                            const float e1 = rmask * ((__uint_as_float(v[j + 1]) + bb.y) - __uint_as_float(tt[j + 1]));
+                            const float e2 = rmask * ((__uint_as_float(v[j + 2]) + bb.z) - __uint_as_float(tt[j + 2]));
+                            const float e3 = rmask * ((__uint_as_float(v[j + 3]) + bb.w) - __uint_as_float(tt[j + 3]));
                             sq = fmaf(e0, e0, sq); sq = fmaf(e1, e1, sq); sq = fmaf(e2, e2, sq); sq = fmaf(e3, e3, sq);
                             dout[j / 2] = pack_bf16(e0 * g.loss_scale, e1 * g.loss_scale);
                             dout[j / 2 + 1] = pack_bf16(e2 * g.loss_scale, e3 * g.loss_scale);
@@ -725,7 +730,7 @@ inline bool use_cluster(int N, int H = 256, int D = 128) {
     const char* e = getenv("NERFATTN_CLUSTER");
     const bool on = e ? atoi(e) != 0 : H >= 512;
     const char* sl = getenv("NERFATTN_CHAIN_SLOTS");
-    return on && !(sl && atoi(sl) == 1) && (N / BM) % 2 == 0 && num_sms() % 2 == 0;
+    return on && !(sl && atoi(sl) == 1) && ceil_div(N, BM) % 2 == 0 && num_sms() % 2 == 0;
 }
 inline size_t scratch_elems(int H, int L) {
     return (size_t)num_sms() * 2 * (L + 1) * BM * H;
@@ -866,7 +871,7 @@ inline int build_fwd_maps(int /*N*/, int H, int L, int nf, const LayerMap& lm, _
 inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
                          const float* u, float* dotpart, cudaStream_t s, const float* pvec = nullptr, float* pvpart = nullptr) {
     ChainArgs a{};
-    a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = N / BM; a.recs = recs;
+    a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = ceil_div(N, BM); a.recs = recs;
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
     a.dotvec = u; a.dotpart = dotpart; a.pvec = pvec; a.pvpart = pvpart;
     a.sincos_mode = sincos_mode();

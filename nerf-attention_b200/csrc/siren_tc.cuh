@@ -225,7 +225,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // split-K (kDw of small groups: one output tile per fit would leave most SMs idle): tile index
     // = (fit, m tile, n tile, K slice), partial results go to separate slots and are summed by Adam
     const int ksplits = (MODE == kDw && g.ksplits > 1) ? g.ksplits : 1;
-    const int num_kb = g.K / BK / ksplits;
+    const int num_kb = ceil_div(g.K, BK) / ksplits;       // kDw: K = N rows, a ragged last block is zero-filled by TMA
     const int total_tiles = g.nb * g.m_tiles * g.n_tiles * ksplits;
 
     if (warp == 0 && lane == 0) {

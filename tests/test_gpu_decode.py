@@ -26,7 +26,7 @@ def test_kvread_qk_matches_torch(cuda_device, n, heads, d):
     assert rel_err(out.cpu(), ref) <= 1e-5          # fp32 accumulate of exact fp16 products
 
 
-@pytest.mark.parametrize('name,n', [('medium', 512), ('tiny', 2048), ('large', 256), ('deep', 1024)])
+@pytest.mark.parametrize('name,n', [('medium', 512), ('tiny', 2048), ('large', 256), ('deep', 1024), ('medium', 333)])
 @pytest.mark.parametrize('precision,tol', [('fp32', 2e-5), ('bf16', 3e-2)])
 def test_decode_qk_matches_oracle(cuda_device, name, n, precision, tol):
     cfg = next(c for c in na.CONFIGS_FULL if c.name == name)
@@ -123,7 +123,7 @@ def test_scaling_experiment_and_layer_profile_outputs(cuda_device, tmp_path):
     assert data['keys'].shape == (2, 256, 128)
 
 
-@pytest.mark.parametrize('name,n', [('medium', 512), ('tiny', 1024), ('large', 256), ('deep', 384)])
+@pytest.mark.parametrize('name,n', [('medium', 512), ('tiny', 1024), ('large', 256), ('deep', 384), ('small', 777)])
 @pytest.mark.parametrize('precision,tol', [('fp32', 5e-5), ('bf16', 3e-2)])
 def test_siren_attention_matches_oracle(cuda_device, name, n, precision, tol):
     """softmax(scale * q.K_hat) @ V_hat from key and value SIRENs against the CPU restatement."""

@@ -218,9 +218,13 @@ def test_argument_validation_without_a_gpu():
     fp32_bytes = need.value
     assert lib.nerfattn_fit_workspace_bytes(fits, 1, 2, ctypes.byref(need)) == 0
     assert 0 < need.value and fp32_bytes > 8 * 2048 * 256 * 4
-    f.N = 2000                                                                              # bf16 needs N % 128 == 0
+    f.N = 2000                                                                              # any N in both modes
+    assert lib.nerfattn_fit_workspace_bytes(fits, 1, 2, ctypes.byref(need)) == 0
+    assert lib.nerfattn_fit_workspace_bytes(fits, 1, 0, ctypes.byref(need)) == 0
+    f.D = 48                                                                                # bf16: D in {64, 128, 256}
     assert lib.nerfattn_fit_workspace_bytes(fits, 1, 2, ctypes.byref(need)) == -2
-    assert lib.nerfattn_fit_workspace_bytes(fits, 1, 0, ctypes.byref(need)) == 0           # fp32 takes any N
+    assert lib.nerfattn_fit_workspace_bytes(fits, 1, 0, ctypes.byref(need)) == 0
+    f.D = 128
     f.H = 30
     assert lib.nerfattn_fit_workspace_bytes(fits, 1, 0, ctypes.byref(need)) == -2
 
