@@ -64,6 +64,7 @@ struct Group {
     // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch
     bool use_chain;
     __nv_bfloat16* chain_scratch;
+    float* psc;            // omega-prescaled W0 / sine-layer biases [nf][(L+2)H]
     chain::ChainMaps* cmaps;
 };
 
@@ -200,6 +201,7 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         g.wbf16 = bf ? ar.take<__nv_bfloat16>((size_t)g.nf * g.lm.P) : nullptr;
         g.maps = nullptr;
         g.chain_scratch = g.use_chain ? ar.take<__nv_bfloat16>(chain::scratch_elems(g.H, g.L)) : nullptr;
+        g.psc = g.use_chain ? ar.take<float>((size_t)g.nf * chain::psc_floats(g.H, g.L)) : nullptr;
         g.cmaps = nullptr;
     }
     plan.bytes = ar.bytes();
@@ -276,6 +278,7 @@ static void launch_adam(const Group& g, const Plan& plan, double beta1, double b
     a.loss_inv_count = 1.0f / ((float)g.N * (float)g.D);
     a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
     a.wbf16 = g.wbf16; a.wbf16_fit = g.lm.P;
+    a.psc = g.psc; a.psc_fit = g.psc ? chain::psc_floats(g.H, g.L) : 0; a.H = g.H; a.L = g.L;
     // 64-thread blocks (3 K registers, no shared memory): small enough to be co-scheduled on SMs whose
     // registers and shared memory are almost entirely held by another group's chain CTA, so this
     // HBM-bound update overlaps that group's issue-bound kernel instead of waiting for free SMs
@@ -527,6 +530,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             if (rc) return rc;
             if (g.use_chain && (rc = chain::build_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.wbf16, g.act, g.cosb, g.dy, *g.cmaps))) return rc;
             tc::mirror_weights(g.d_recs, g.lm, g.nf, g.wbf16, stream);
+            if (g.psc) chain::scale_params(g.d_recs, g.nf, g.H, g.L, g.psc, stream);
             NA_LAUNCH_OK("mirror_weights");
         }
     }
@@ -551,7 +555,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
                 int r2 = g.use_chain
                     ? chain::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, *g.cmaps, g.act, g.cosb, g.dy,
                                    g.chain_scratch, g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                   g.losspart_per_fit, g.mtiles, af, g.nsplit, s)
+                                   g.losspart_per_fit, g.mtiles, af, g.nsplit, g.psc, s)
                     : tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
                                 g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
                                 g.losspart_per_fit, g.mtiles, s);
@@ -635,6 +639,7 @@ struct InferPlan {
     Group g;
     float** d_out;        // device array of per-model output pointers
     float* u; float* c0;  // decode: folded query
+    float* psc;           // decode, chain path: omega-prescaled W0 / biases
     float* dotpart; int nparts;
     size_t bytes;
 };
@@ -665,13 +670,14 @@ static void infer_plan(const na_fit_t* m, int n, int precision, bool decode, voi
     g.act[0] = ar.take<char>(nh * (bf ? 2 : 4));
     g.act[1] = ar.take<char>(nh * (bf ? 2 : 4));
     g.wbf16 = bf ? ar.take<__nv_bfloat16>((size_t)n * g.lm.P) : nullptr;
-    p.u = p.c0 = p.dotpart = nullptr; p.nparts = 0;
+    p.u = p.c0 = p.dotpart = p.psc = nullptr; p.nparts = 0;
     if (decode) {
         p.u = ar.take<float>((size_t)n * g.H);
         p.c0 = ar.take<float>(n);
         const bool dchain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
         p.nparts = dchain ? chain::decode_parts(g.H) : bf ? (g.H / tc::hidden_bn(g.H)) * 2 : ceil_div(g.H, f32::BN);
         p.dotpart = ar.take<float>((size_t)n * p.nparts * g.N);
+        p.psc = dchain ? ar.take<float>((size_t)n * chain::psc_floats(g.H, g.L)) : nullptr;
     }
     p.bytes = ar.bytes();
 }
@@ -751,6 +757,7 @@ extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void*
     if (!reuse_setup) {
         if ((rc = infer_upload(models, n, p, scores, stream))) return rc;
         if (bf) { tc::mirror_weights(g.d_recs, g.lm, n, g.wbf16, stream); NA_LAUNCH_OK("mirror_weights"); }
+        if (p.psc) { chain::scale_params(g.d_recs, n, g.H, g.L, p.psc, stream); NA_LAUNCH_OK("scale_params"); }
     }
     dec::decode_prep_kernel<<<n, 256, 0, stream>>>(g.d_recs, (const __half*)q_fp16, g.D, g.H, g.lm.w_off[g.L + 1],
                                                    g.lm.b_off[g.L + 1], p.u, p.c0);
@@ -777,7 +784,7 @@ extern "C" int nerfattn_decode_qk(const na_fit_t* models, int32_t n, const void*
         if ((rc = chain::configure_all())) return rc;
         chain::ChainMaps cm;
         if ((rc = chain::build_fwd_maps(g.N, g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
-        if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, p.u, p.dotpart, stream))) return rc;
+        if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, p.psc, p.u, p.dotpart, stream))) return rc;
     } else {
         const int bn = tc::hidden_bn(g.H);
         {
@@ -837,6 +844,7 @@ struct PvPlan {
     float* vfull;          // fp32 mode: reconstructed values [n][N][D]
     float** d_out;         // fp32 mode: per-model output pointers into vfull
     bool chain;
+    float* psc;
     size_t bytes;
 };
 static void pv_plan(const na_fit_t* m, int n, int N, int D, int precision, void* ws, PvPlan& p) {
@@ -858,6 +866,7 @@ static void pv_plan(const na_fit_t* m, int n, int N, int D, int precision, void*
     if (p.chain) {
         g.wbf16 = ar.take<__nv_bfloat16>((size_t)n * g.lm.P);
         p.partial = ar.take<float>((size_t)n * (g.mtiles * 4) * g.H);
+        p.psc = ar.take<float>((size_t)n * chain::psc_floats(g.H, g.L));
     } else {
         const size_t nh = (size_t)n * g.N * g.H;
         g.act[0] = ar.take<char>(nh * 4);
@@ -936,10 +945,11 @@ extern "C" int nerfattn_decode_pv(const na_fit_t* models, int32_t n, const float
         // V never exists: the forward chain reduces p_t * h_L(t) over the positions, the output layer acts on the sum
         if ((rc = tc::configure_all()) || (rc = chain::configure_all())) return rc;
         tc::mirror_weights(g.d_recs, g.lm, n, g.wbf16, stream);
+        chain::scale_params(g.d_recs, n, g.H, g.L, pl.psc, stream);
         NA_LAUNCH_OK("mirror_weights");
         chain::ChainMaps cm;
         if ((rc = chain::build_fwd_maps(g.N, g.H, g.L, n, g.lm, g.wbf16, cm))) return rc;
-        if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, nullptr, nullptr, stream, p, pl.partial))) return rc;
+        if ((rc = chain::launch_decode(g.N, g.D, g.H, g.L, n, g.lm, g.d_recs, cm, pl.psc, nullptr, nullptr, stream, p, pl.partial))) return rc;
         dec::attn_finish_kernel<<<n, 256, g.H * sizeof(float), stream>>>(g.d_recs, pl.partial, g.mtiles * 4, g.H, g.D,
                                                                          g.lm.w_off[g.L + 1], g.lm.b_off[g.L + 1], out);
         NA_LAUNCH_OK("attn_finish_kernel");

@@ -69,6 +69,7 @@ struct ChainArgs {
     float* losspart; int losspart_per_fit; float loss_scale;
     const float* dotvec; float* dotpart;    // forward-only (decode): u [nf][H] fp32, partial scores [nf][CG][N]
     const float* pvec; float* pvpart;       // forward-only (decode, values): p [nf][N] fp32, partial sums [nf][N/32][H]
+    const float* psc; int psc_fit;          // per fit w*W0[H], w*b0[H], w*b_1[H] .. w*b_L[H] (scale_params_kernel; Adam keeps it current)
     int dbg;                                // NERFATTN_CHAIN_DBG (profiling experiments only)
     int sincos_mode;                        // bit 0: hidden layers, bit 1: layer 0 use the MUFU-core sincos (common.cuh)
 };
@@ -497,8 +498,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
                     const float x = __ldg(rec->pos + row_c);
-                    const float* w0 = rec->params + g.w_off[0] + col0;
-                    const float* b0 = rec->params + g.b_off[0] + col0;
+                    // omega-prescaled layer-0 weights / biases (kept current by Adam): one FFMA per argument
+                    const float* w0 = g.psc + (size_t)fit * g.psc_fit + col0;
+                    const float* b0 = g.psc + (size_t)fit * g.psc_fit + H + col0;
                     float4 wn[2], bn[2];                         // weights / biases of the next 8 columns
                     wn[0] = __ldg(reinterpret_cast<const float4*>(w0)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0) + 1);
                     bn[0] = __ldg(reinterpret_cast<const float4*>(b0)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0) + 1);
@@ -510,8 +512,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             float arg[8], sn[8], cs[8];
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
-                                arg[4 * j] = omega * fmaf(x, wn[j].x, bn[j].x); arg[4 * j + 1] = omega * fmaf(x, wn[j].y, bn[j].y);
-                                arg[4 * j + 2] = omega * fmaf(x, wn[j].z, bn[j].z); arg[4 * j + 3] = omega * fmaf(x, wn[j].w, bn[j].w);
+                                arg[4 * j] = fmaf(x, wn[j].x, bn[j].x); arg[4 * j + 1] = fmaf(x, wn[j].y, bn[j].y);
+                                arg[4 * j + 2] = fmaf(x, wn[j].z, bn[j].z); arg[4 * j + 3] = fmaf(x, wn[j].w, bn[j].w);
                             }
                             const int nxt = (u * 2 + gi + 1 < NU * 2) ? (u * 2 + gi + 1) * 8 : 0;
                             wn[0] = __ldg(reinterpret_cast<const float4*>(w0 + nxt)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0 + nxt) + 1);
@@ -528,7 +530,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     }
                 } else if (s <= L) {
                     // ---------------- hidden sine layer s
-                    const float* bsrc = rec->params + g.b_off[s] + col0;
+                    const float* bsrc = g.psc + (size_t)fit * g.psc_fit + (size_t)(s + 1) * H + col0;
                     float4 bn[4];                                // bias of the next 16 columns (L1-resident)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc) + j);
@@ -547,10 +549,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            arg[4 * j] = omega * (__uint_as_float(v[4 * j]) + bn[j].x);
-                            arg[4 * j + 1] = omega * (__uint_as_float(v[4 * j + 1]) + bn[j].y);
-                            arg[4 * j + 2] = omega * (__uint_as_float(v[4 * j + 2]) + bn[j].z);
-                            arg[4 * j + 3] = omega * (__uint_as_float(v[4 * j + 3]) + bn[j].w);
+                            arg[4 * j] = fmaf(__uint_as_float(v[4 * j]), omega, bn[j].x);
+                            arg[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), omega, bn[j].y);
+                            arg[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), omega, bn[j].z);
+                            arg[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), omega, bn[j].w);
                         }
                         if (u + 1 < NU) {                        // in flight during the sincos below
                             tmem_ld16(t_row + (u + 1) * 16, v);
@@ -813,6 +815,22 @@ inline int phase_mask() {
 
 // One training epoch of one group: the chain, then the dW GEMMs (contraction over all rows of a fit)
 // and the layer-0 gradient; Adam follows in the caller.
+// omega-prescaled layer-0 weights and all sine-layer biases (one FFMA per sine argument): [n][(L + 2) * H]
+__global__ void scale_params_kernel(const FitRec* recs, int H, int L, const int* /*unused*/, float* psc) {
+    const FitRec& rec = recs[blockIdx.x];
+    float* dst = psc + (size_t)blockIdx.x * (L + 2) * H;
+    const int per = H * H + H;                                   // one hidden layer in the packed vector
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        dst[j] = rec.omega * rec.params[j];                      // W0
+        dst[H + j] = rec.omega * rec.params[H + j];              // b0
+        for (int l = 1; l <= L; ++l) dst[(l + 1) * H + j] = rec.omega * rec.params[2 * H + (l - 1) * per + H * H + j];
+    }
+}
+inline size_t psc_floats(int H, int L) { return (size_t)(L + 2) * H; }
+inline void scale_params(const FitRec* recs, int n, int H, int L, float* psc, cudaStream_t s) {
+    scale_params_kernel<<<n, 256, 0, s>>>(recs, H, L, nullptr, psc);
+}
+
 struct AdamFuse {            // non-null epoch => the dW epilogues apply Adam to layers 1..L+1 (siren_tc.cuh)
     const int* epoch; const float* step_size; const float* bc2; float beta1, beta2, eps;
     __nv_bfloat16* wbf16;
@@ -824,7 +842,7 @@ inline bool adam_fused() { const char* e = getenv("NERFATTN_ADAM_FUSED"); return
 inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const GroupMaps& m,
                  const ChainMaps& cm, void* const* act, void* const* dzs, void* dy, __nv_bfloat16* scratch,
                  float* gradpart, float* colpart, const size_t* colpart_layer_off, float* xpart, float* losspart,
-                 int losspart_per_fit, int mtiles, const AdamFuse& af, int ksplits, cudaStream_t s) {
+                 int losspart_per_fit, int mtiles, const AdamFuse& af, int ksplits, const float* psc, cudaStream_t s) {
     int rc;
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
@@ -834,6 +852,7 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
     a.losspart = losspart; a.losspart_per_fit = losspart_per_fit;
     a.loss_scale = 2.0f / ((float)N * (float)D);
     a.sincos_mode = sincos_mode();
+    a.psc = psc; a.psc_fit = (int)psc_floats(H, L);
     { const char* e = getenv("NERFATTN_CHAIN_DBG"); a.dbg = e ? atoi(e) : 0; }
     const int phases = phase_mask();
     if ((phases & 1) && (rc = launch(H, cm, a, 0, s))) return rc;
@@ -852,6 +871,7 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
             w.adam_beta1 = af.beta1; w.adam_beta2 = af.beta2; w.adam_eps = af.eps;
             w.adam_w_off = lm.w_off[l]; w.adam_b_off = lm.b_off[l];
             w.adam_wbf16 = af.wbf16; w.adam_wbf16_fit = lm.P;
+            if (l <= L) { w.adam_psc = const_cast<float*>(psc); w.adam_psc_fit = psc_floats(H, L); w.adam_psc_off = (l + 1) * H; }
         }
         if ((rc = launch_bn<kDw, true, true>(dw_bn(H), m.dw[l], w, s))) return rc;
     }
@@ -869,11 +889,13 @@ inline int build_fwd_maps(int /*N*/, int H, int L, int nf, const LayerMap& lm, _
     return NA_OK;
 }
 inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
-                         const float* u, float* dotpart, cudaStream_t s, const float* pvec = nullptr, float* pvpart = nullptr) {
+                         const float* psc, const float* u, float* dotpart, cudaStream_t s, const float* pvec = nullptr,
+                         float* pvpart = nullptr) {
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = ceil_div(N, BM); a.recs = recs;
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
     a.dotvec = u; a.dotpart = dotpart; a.pvec = pvec; a.pvpart = pvpart;
+    a.psc = psc; a.psc_fit = (int)psc_floats(H, L);
     a.sincos_mode = sincos_mode();
     return launch(H, cm, a, pvec ? 2 : 1, s);
 }

@@ -401,6 +401,7 @@ struct AdamArgs {
     float beta1, beta2, eps;
     // BF16 copies of the hidden/output weights for the tensor path (nullptr in fp32 mode)
     __nv_bfloat16* wbf16; size_t wbf16_fit;
+    float* psc; size_t psc_fit; int H, L;   // chain mode: omega-prescaled copies of W0 / the sine-layer biases to refresh
     int p_end;              // parameters [0, p_end) are updated here (the rest in the dW epilogues when fused)
 };
 
@@ -458,6 +459,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     *reinterpret_cast<float4*>(rec.m + p) = make_float4(m[0], m[1], m[2], m[3]);
     *reinterpret_cast<float4*>(rec.v + p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(rec.params + p) = make_float4(w[0], w[1], w[2], w[3]);
+    if (a.psc && (layer == 0 || (is_bias && layer <= a.L))) {       // what the chain kernel's sine arguments read
+        float* dst = a.psc + (size_t)f * a.psc_fit + (layer == 0 ? p : (layer + 1) * a.H + (p - a.lm.b_off[layer]));
+        *reinterpret_cast<float4*>(dst) = make_float4(rec.omega * w[0], rec.omega * w[1], rec.omega * w[2], rec.omega * w[3]);
+    }
     if (a.wbf16 && layer >= 1 && !is_bias) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
         *reinterpret_cast<uint2*>(a.wbf16 + (size_t)f * a.wbf16_fit + p) =

@@ -68,6 +68,7 @@ struct TcArgs {
     float adam_beta1, adam_beta2, adam_eps;
     int adam_w_off, adam_b_off;                           // offsets of W_l / b_l in the packed parameter vector
     __nv_bfloat16* adam_wbf16; size_t adam_wbf16_fit;     // bf16 mirror the MMAs read
+    float* adam_psc; size_t adam_psc_fit; int adam_psc_off;   // omega-prescaled bias copy the chain kernel reads (or null)
     const float* dotvec; size_t dotvec_fit;               // kFwdDot: u [N] per fit (fp32)
     float* dotpart; size_t dotpart_fit;                   // kFwdDot: [n_tiles*2][M] partial row sums
 };
@@ -523,6 +524,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), adam_bc2v), g.adam_eps);
                         ww = __fadd_rn(ww, __fdiv_rn(__fmul_rn(adam_nss, mm), denom));
                         rec->m[pi] = mm; rec->v[pi] = vv; rec->params[pi] = ww;
+                        if (g.adam_psc) g.adam_psc[(size_t)b * g.adam_psc_fit + g.adam_psc_off + row] = rec->omega * ww;
                     } else g.biasgrad[(size_t)b * g.biasgrad_fit + (size_t)ks * g.M + row] = __uint_as_float(dbv);
                 }
             }
