@@ -65,7 +65,7 @@ struct ChainArgs {
     int N, D, L, nf, mtiles;
     const FitRec* recs;
     int w_off[kMaxLayers], b_off[kMaxLayers];
-    __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][128][H]
+    __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][H/16][128][16]
     float* losspart; int losspart_per_fit; float loss_scale;
     const float* dotvec; float* dotpart;    // forward-only (decode): u [nf][H] fp32, partial scores [nf][CG][N]
     const float* pvec; float* pvpart;       // forward-only (decode, values): p [nf][N] fp32, partial sums [nf][N/32][H]
@@ -465,7 +465,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         const bool mufu_hidden = (g.sincos_mode & 1) != 0, mufu_l0 = (g.sincos_mode & 2) != 0;
         const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
         const uint32_t t_row = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + col0;
-        __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H) + (size_t)r * H + col0;
+        // cos scratch of one layer: [H/16 units][128 rows][16 columns], so that the 32 lanes of a warp (consecutive
+        // rows, 32 B each) touch 1 KB of contiguous memory per access instead of 32 lines at row stride
+        constexpr int SCR_U = BM * 16;                // elements between consecutive 16-column units
+        __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H) + (size_t)(col0 / 16) * SCR_U + r * 16;
         uint32_t acc_phase = 0, free_phase = 0;
 #ifdef NA_CHAIN_TIMING
         long long t_acc = 0, t_kind[4] = {0, 0, 0, 0}, t_begin = clock64(), tq = 0, ts = 0, t_acc0 = 0;
@@ -526,7 +529,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             }
                         }
                         act_store16(act_u32, r, col0 + u * 16, so);
-                        if (!FWD) st_global_256_hint(scr + u * 16, co, pol_keep);
+                        if (!FWD) st_global_256_hint(scr + u * SCR_U, co, pol_keep);
                     }
                 } else if (s <= L) {
                     // ---------------- hidden sine layer s
@@ -584,7 +587,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         }
                         if (!(FWD && s == L)) {
                             act_store16(act_u32, r, col0 + u * 16, so);
-                            if (!FWD) st_global_256_hint(cdst + u * 16, co, pol_keep);
+                            if (!FWD) st_global_256_hint(cdst + u * SCR_U, co, pol_keep);
                         } else if (MODE == 2) {
                             // sum the 16 columns over the 32 rows of this warp: transpose-reduce, 16 shuffles
                             float w8[8], w4[4], w2[2];
@@ -662,7 +665,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     const __nv_bfloat16* csrc = scr + (size_t)lp * (BM * H);
                     uint32_t cc[PFD][8];
 #pragma unroll
-                    for (int p = 0; p < PFD; ++p) ld_global_256_hint(csrc + p * 16, cc[p], pol_keep);
+                    for (int p = 0; p < PFD; ++p) ld_global_256_hint(csrc + p * SCR_U, cc[p], pol_keep);
                     NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
                     if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
                     NA_T1();
@@ -682,7 +685,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * c0),
                                                 __uint_as_float(v[2 * t + 1]) * (omega * c1));
                         }
-                        if (u + PFD < NU) ld_global_256_hint(csrc + (u + PFD) * 16, cc[u % PFD], pol_keep);
+                        if (u + PFD < NU) ld_global_256_hint(csrc + (u + PFD) * SCR_U, cc[u % PFD], pol_keep);
                         act_store16(act_u32, r, col0 + u * 16, dout);
                     }
                 }
