@@ -117,6 +117,14 @@ def forward(state: dict[str, torch.Tensor], omega_0: float, x: torch.Tensor) -> 
     return F.linear(h, wf, bf)
 
 
+def forward_exact(state: dict[str, torch.Tensor], omega_0: float, x: torch.Tensor) -> torch.Tensor:
+    """The same fp32 weights and fp32 inputs evaluated in float64: the function that every fp32 evaluation
+    (the reference's torch CPU arithmetic, the CUDA kernels) approximates.  Parity tests use it to tell the
+    kernel's rounding error from the reference's own (torch's CPU fp32 path is usually within 1e-6 of it, but
+    has been seen 3e-5 off in the first evaluation of a process that had just initialised CUDA)."""
+    return forward({k: v.double() for k, v in state.items()}, omega_0, x.double())
+
+
 def count_parameters(state: dict[str, torch.Tensor]) -> int:
     """nerf_attention/siren.py:63-64."""
     return sum(int(t.numel()) for t in state.values())
@@ -258,11 +266,17 @@ def adam_reference_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: to
 # --------------------------------------------------------------------------
 
 def decode_scores(state: dict[str, torch.Tensor], omega_0: float, mean: torch.Tensor,
-                  std: torch.Tensor, q: torch.Tensor, seq_len: int) -> torch.Tensor:
+                  std: torch.Tensor, q: torch.Tensor, seq_len: int, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """q . K_hat[n] for every cached position, with K_hat = SIREN(pos)*std+mean
-    (reconstruction as in nerf_attention/evaluate.py:148-152)."""
-    k_hat = forward(state, omega_0, positions_for(seq_len)) * std + mean
-    return k_hat @ q.float()
+    (reconstruction as in nerf_attention/evaluate.py:148-152).
+
+    ``dtype=torch.float64`` evaluates the same fp32 weights and fp32 position grid in double precision: the
+    exact function both fp32 evaluations (the reference's torch CPU arithmetic and the CUDA kernels)
+    approximate.  With omega_0 = 30 per sine layer, fp32 rounding differences are amplified to a few 1e-5
+    relative, so fp32 parity tests bound the kernel's error against this truth by the reference's own."""
+    state = {k: v.to(dtype) for k, v in state.items()}
+    k_hat = forward(state, omega_0, positions_for(seq_len).to(dtype)) * std.to(dtype) + mean.to(dtype)
+    return k_hat @ q.to(dtype)
 
 
 def kvread_scores(k_fp16: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
@@ -272,13 +286,16 @@ def kvread_scores(k_fp16: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
 
 def decode_attention(key_state: dict[str, torch.Tensor], value_state: dict[str, torch.Tensor], omega_k: float,
                      omega_v: float, mean_k: torch.Tensor, std_k: torch.Tensor, mean_v: torch.Tensor,
-                     std_v: torch.Tensor, q: torch.Tensor, seq_len: int, scale: float) -> torch.Tensor:
+                     std_v: torch.Tensor, q: torch.Tensor, seq_len: int, scale: float,
+                     dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """softmax(scale * q.K_hat) @ V_hat with both caches reconstructed from their SIRENs (the decode
-    the reference describes in README.md:3-8; reconstruction as in evaluate.py:148-152)."""
-    pos = positions_for(seq_len)
-    k_hat = forward(key_state, omega_k, pos) * std_k + mean_k
-    v_hat = forward(value_state, omega_v, pos) * std_v + mean_v
-    p = torch.softmax(scale * (k_hat @ q.float()), dim=0)
+    the reference describes in README.md:3-8; reconstruction as in evaluate.py:148-152).
+    ``dtype=torch.float64``: the exact function of the same fp32 weights (see ``forward_exact``)."""
+    pos = positions_for(seq_len).to(dtype)
+    cast = lambda st: {k: v.to(dtype) for k, v in st.items()}
+    k_hat = forward(cast(key_state), omega_k, pos) * std_k.to(dtype) + mean_k.to(dtype)
+    v_hat = forward(cast(value_state), omega_v, pos) * std_v.to(dtype) + mean_v.to(dtype)
+    p = torch.softmax(scale * (k_hat @ q.to(dtype)), dim=0)
     return p @ v_hat
 
 
