@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NERFATTN_ABI_VERSION 7
+#define NERFATTN_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define NA_API __attribute__((visibility("default")))
@@ -199,6 +199,26 @@ NA_API int nerfattn_kvread_pv(const void* v_fp16, const float* p, float* out, in
                        void* workspace, size_t workspace_bytes, na_stream_t stream);
 NA_API int nerfattn_decode_pv(const na_fit_t* value_models, int32_t n, const float* p, float* out,
                        int32_t precision, void* workspace, size_t workspace_bytes, na_stream_t stream);
+
+/*
+ * Synthetic KV-cache generator.
+ * Replaces the per-(layer, head) body of extract_kv_cache_synthetic, nerf_attention/extract.py:199-237:
+ * one numpy legacy RandomState(seed) stream per entry (seed = layer * num_kv_heads + head, :207), consumed in
+ * the reference's order; n_spikes = int(3 * sharpness) and max_width = max(2, int(5 / sharpness)) with
+ * sharpness = 1 + 2 * layer / max(num_layers - 1, 1) (:204,:222-224) are computed by the caller.
+ * positions: DEVICE fp32 [N] = torch.linspace(0, 1, N) (:197).  keys / values: DEVICE fp32 [N][D] out
+ * (one head of layer_XX.pt's [kv_heads, N, D] tensors).  `streams` itself is a HOST array.
+ * Results agree with the CPU generator to float32 rounding of the smooth terms (libm / numpy sin, cos, log and
+ * exp differ from CUDA's in the last place); the random stream itself is reproduced exactly.
+ */
+typedef struct na_synth_stream {
+    uint32_t seed;
+    int32_t n_spikes, max_width;
+    float* keys; float* values;
+} na_synth_stream_t;
+NA_API int nerfattn_synth_workspace_bytes(int32_t nstreams, int32_t N, int32_t D, size_t* bytes);
+NA_API int nerfattn_synth_kv(const na_synth_stream_t* streams, int32_t nstreams, int32_t N, int32_t D,
+                      const float* positions, void* workspace, size_t workspace_bytes, na_stream_t stream);
 
 /*
  * Diagnostic: C[M,N] (fp32) = A x B with BF16 operands through the same

@@ -21,6 +21,7 @@
 #include "siren_tc.cuh"
 #include "siren_chain.cuh"
 #include "decode.cuh"
+#include "synth.cuh"
 
 namespace na {
 
@@ -1000,6 +1001,58 @@ __global__ void debug_sincos_kernel(const float* x, float* s, float* c, long lon
     s[i] = sv[0]; c[i] = cv[0];
 }
 }  // namespace na
+
+// ---------------------------------------------------------------------------
+// synthetic KV generator (synth.cuh; reference nerf_attention/extract.py:182-259)
+namespace na {
+struct SynthPlan { synth::Stream* d_streams; float** d_keys; float** d_values; float* staging; size_t bytes; };
+static void synth_plan(int nstreams, int N, int D, void* ws, SynthPlan& p) {
+    Arena ar(ws);
+    p.d_streams = ar.take<synth::Stream>(nstreams);
+    p.d_keys = ar.take<float*>(nstreams);
+    p.d_values = ar.take<float*>(nstreams);
+    p.staging = ar.take<float>((size_t)nstreams * 2 * N * D);
+    p.bytes = ar.bytes();
+}
+}  // namespace na
+
+extern "C" int nerfattn_synth_workspace_bytes(int32_t nstreams, int32_t N, int32_t D, size_t* bytes) {
+    if (!bytes || nstreams <= 0 || N <= 0 || D <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    SynthPlan p; synth_plan(nstreams, N, D, nullptr, p);
+    *bytes = p.bytes;
+    return NA_OK;
+}
+
+extern "C" int nerfattn_synth_kv(const na_synth_stream_t* streams, int32_t nstreams, int32_t N, int32_t D,
+                                 const float* positions, void* workspace, size_t workspace_bytes, na_stream_t stream_) {
+    if (!streams || !positions || nstreams <= 0 || N <= 0 || D <= 0) { set_error("bad argument"); return NA_ERR_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SynthPlan p; synth_plan(nstreams, N, D, workspace, p);
+    if (!workspace || workspace_bytes < p.bytes) { set_error("workspace too small: need %zu bytes", p.bytes); return NA_ERR_WORKSPACE; }
+    std::vector<synth::Stream> hs(nstreams);
+    std::vector<float*> hk(nstreams), hv(nstreams);
+    for (int i = 0; i < nstreams; ++i) {
+        const na_synth_stream_t& st = streams[i];
+        if (!st.keys || !st.values) { set_error("stream %d: null output", i); return NA_ERR_INVALID; }
+        if (st.n_spikes < 0 || st.n_spikes > synth::kMaxSpikes || st.max_width < 2) {
+            set_error("stream %d: n_spikes must be in [0, %d] and max_width >= 2", i, synth::kMaxSpikes);
+            return NA_ERR_UNSUPPORTED;
+        }
+        hs[i].seed = st.seed; hs[i].n_spikes = st.n_spikes; hs[i].max_width = st.max_width;
+        hs[i].keys_t = p.staging + (size_t)(2 * i) * N * D;
+        hs[i].values_t = p.staging + (size_t)(2 * i + 1) * N * D;
+        hk[i] = st.keys; hv[i] = st.values;
+    }
+    NA_CUDA_OK(cudaMemcpyAsync(p.d_streams, hs.data(), nstreams * sizeof(synth::Stream), cudaMemcpyHostToDevice, stream));
+    NA_CUDA_OK(cudaMemcpyAsync(p.d_keys, hk.data(), nstreams * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    NA_CUDA_OK(cudaMemcpyAsync(p.d_values, hv.data(), nstreams * sizeof(float*), cudaMemcpyHostToDevice, stream));
+    synth::synth_kv_kernel<<<nstreams, synth::kThreads, 0, stream>>>(p.d_streams, positions, N, D);
+    NA_LAUNCH_OK("synth_kv_kernel");
+    synth::TransposeArgs ta{p.d_streams, p.d_keys, p.d_values, N, D};
+    synth::transpose_kernel<<<dim3(ceil_div(N, 32), ceil_div(D, 32), 2 * nstreams), dim3(32, 8), 0, stream>>>(ta);
+    NA_LAUNCH_OK("synth transpose_kernel");
+    return NA_OK;
+}
 
 extern "C" int nerfattn_debug_sincos(const float* x, float* s, float* c, int64_t n, int32_t mode, na_stream_t stream_) {
     if (!x || !s || !c || n <= 0 || (mode != 0 && mode != 1)) { set_error("bad argument"); return NA_ERR_INVALID; }

@@ -11,7 +11,7 @@ import ctypes
 import os
 from pathlib import Path
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'bf16': PREC_BF16}
@@ -32,6 +32,12 @@ class NaFit(ctypes.Structure):
         ('params', c_void_p), ('adam_m', c_void_p), ('adam_v', c_void_p), ('losses', c_void_p),
         ('cos_sims', c_void_p), ('per_pos_mse', c_void_p), ('scalars', c_void_p),
     ]
+
+
+class NaSynthStream(ctypes.Structure):
+    """struct na_synth_stream (include/nerfattn.h)."""
+    _fields_ = [('seed', ctypes.c_uint32), ('n_spikes', c_int32), ('max_width', c_int32),
+                ('keys', c_void_p), ('values', c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -69,6 +75,9 @@ _SIGNATURES = {
                                      c_void_p]),
     'nerfattn_decode_pv': (c_int32, [ctypes.POINTER(NaFit), c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                      c_size_t, c_void_p]),
+    'nerfattn_synth_workspace_bytes': (c_int32, [c_int32, c_int32, c_int32, ctypes.POINTER(c_size_t)]),
+    'nerfattn_synth_kv': (c_int32, [ctypes.POINTER(NaSynthStream), c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
     'nerfattn_debug_gemm_bf16': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_void_p]),
     'nerfattn_debug_sincos': (c_int32, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_void_p]),
