@@ -39,21 +39,46 @@ def sweep_selection(metadata: KVMetadata, quick: bool) -> tuple[list[int], int, 
     return sorted({l for l in layers if l < nl}), heads, configs
 
 
+def enumerate_job_specs(layers: list[int], heads: int, configs: list[SIRENConfig]) -> list[dict]:
+    """Jobs in the reference's loop order: layer -> head -> key, value -> config (fit.py:54-65); no tensors yet."""
+    return [{'name': f"L{layer_idx}_H{head_idx}_{kv_type}_{config.name}", 'layer': layer_idx, 'head': head_idx,
+             'kv_type': kv_type, 'config': config, 'config_index': ci, 'tensor': None}
+            for layer_idx in layers for head_idx in range(heads) for kv_type in ('key', 'value')
+            for ci, config in enumerate(configs)]
+
+
 def enumerate_jobs(layer_tensors: dict[int, dict[str, torch.Tensor]], layers: list[int], heads: int,
                    configs: list[SIRENConfig]) -> list[dict]:
-    """Jobs in the reference's loop order: layer -> head -> key, value -> config (fit.py:54-65)."""
-    jobs = []
-    for layer_idx in layers:
-        if layer_idx not in layer_tensors:
-            continue
-        blob = layer_tensors[layer_idx]
-        for head_idx in range(heads):
-            for kv_type, tensor in (('key', blob['keys'][head_idx]), ('value', blob['values'][head_idx])):
-                for ci, config in enumerate(configs):
-                    jobs.append({'name': f"L{layer_idx}_H{head_idx}_{kv_type}_{config.name}",
-                                 'layer': layer_idx, 'head': head_idx, 'kv_type': kv_type,
-                                 'config': config, 'config_index': ci, 'tensor': tensor})
+    """The same with each job's [seq_len, d_head] tensor attached (layers without a file are skipped)."""
+    jobs = enumerate_job_specs([l for l in layers if l in layer_tensors], heads, configs)
+    for job in jobs:
+        job['tensor'] = layer_tensors[job['layer']]['keys' if job['kv_type'] == 'key' else 'values'][job['head']]
     return jobs
+
+
+def load_layers_async(kv_dir: Path, layers: list[int], pin: bool):
+    """Start reading ``layer_XX.pt`` files (reference format, extract.py:159-162,241-244) on a thread pool and
+    return {layer: Future[{'keys','values'}]}.  Files are memory-mapped and copied once into pinned host memory, so
+    the upload in nerf_attention.batched is an asynchronous DMA; the caller builds its models meanwhile."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def load(path):
+        try:
+            blob = torch.load(path, map_location='cpu', weights_only=True, mmap=True)
+        except (RuntimeError, ValueError):                # legacy (non-zip) serialisation cannot be mapped
+            blob = torch.load(path, map_location='cpu', weights_only=True)
+        out = {}
+        for k in ('keys', 'values'):
+            t = blob[k] if blob[k].dtype == torch.float32 else blob[k].float()
+            out[k] = t.pin_memory() if pin else t
+        return out
+
+    if not layers:
+        return {}
+    pool = ThreadPoolExecutor(max_workers=min(8, len(layers)), thread_name_prefix='kv-load')
+    futures = {l: pool.submit(load, Path(kv_dir) / f'layer_{l:02d}.pt') for l in layers}
+    pool.shutdown(wait=False)
+    return futures
 
 
 def fit_kv_cache(
@@ -85,37 +110,48 @@ def fit_kv_cache(
         print(f"Device: {device}, Epochs: {epochs}")
 
     layers, heads, configs = sweep_selection(metadata, quick)
-    layer_tensors = {}
+    present = []
     for layer_idx in layers:
-        path = kv_dir / f'layer_{layer_idx:02d}.pt'
-        if not path.exists():
-            if chatty:
-                print(f"  Skipping layer {layer_idx} (not found)")
-            continue
-        layer_tensors[layer_idx] = torch.load(path, map_location='cpu', weights_only=True)
-    jobs = enumerate_jobs(layer_tensors, layers, heads, configs)
+        if (kv_dir / f'layer_{layer_idx:02d}.pt').exists():
+            present.append(layer_idx)
+        elif chatty:
+            print(f"  Skipping layer {layer_idx} (not found)")
+    jobs = enumerate_job_specs(present, heads, configs)
     total = len(layers) * heads * 2 * len(configs)
 
     mine = list(range(len(jobs)))
     if distributed and world > 1:
-        costs = [j['config'].flops_per_epoch(*j['tensor'].shape) for j in jobs]
+        costs = [j['config'].flops_per_epoch(metadata.seq_len, metadata.head_dim) for j in jobs]
         keys = [(j['layer'], j['head'], j['kv_type']) for j in jobs]
         mine = sharding.shard_jobs(keys, costs, world)[rank]
+    mine_set = set(mine)
+
+    # each rank reads only the layer files its shard touches, in the background (pinned host memory)
+    pending = load_layers_async(kv_dir, sorted({jobs[i]['layer'] for i in mine}),
+                                pin=torch.device(device).type == 'cuda' and torch.cuda.is_available())
 
     # Model construction consumes torch's CPU generator in job order (reference fit.py:70 ->
     # siren.py:89).  Unseeded, every rank builds every model so that the stream -- and hence each
     # job's initial weights -- does not depend on the sharding; with per-job seeds only the
-    # local jobs need building.
-    fit_jobs: dict[int, FitJob] = {}
+    # local jobs need building.  The files load meanwhile.
+    models: dict[int, SIREN] = {}
     for i, job in enumerate(jobs):
         if seed_fn is not None:
-            if i not in set(mine):
+            if i not in mine_set:
                 continue
             seed = seed_fn(job)
             if seed is not None:
                 torch.manual_seed(seed)
-        fit_jobs[i] = FitJob(job['tensor'], job['config'],
-                             SIREN(job['config'], out_features=job['tensor'].shape[1]), job['name'])
+        models[i] = SIREN(job['config'], out_features=metadata.head_dim)
+
+    layer_tensors = {l: f.result() for l, f in pending.items()}
+    fit_jobs: dict[int, FitJob] = {}
+    for i in mine:
+        job = jobs[i]
+        job['tensor'] = layer_tensors[job['layer']]['keys' if job['kv_type'] == 'key' else 'values'][job['head']]
+        if job['tensor'].shape[1] != metadata.head_dim:   # metadata.json disagrees with the file: trust the file
+            models[i] = SIREN(job['config'], out_features=job['tensor'].shape[1])
+        fit_jobs[i] = FitJob(job['tensor'], job['config'], models[i], job['name'])
 
     # the fits train concurrently, so the reference's per-fit progress lines (siren.py:112-115) are
     # collected on the device and printed with each fit's record below

@@ -254,3 +254,23 @@ def test_crossover_fit_reproduces_reference_published_numbers():
     assert got['crossover_4060_tokens'] == pytest.approx(want['crossover_4060_tokens'], rel=1e-6)
     assert got['crossover_h100_tokens'] == pytest.approx(want['crossover_h100_tokens'], rel=1e-6)
     assert got['siren_scaling'] == want['siren_scaling']
+
+
+def test_async_layer_loader_and_job_specs(tmp_path):
+    """layer_XX.pt files (reference format) come back unchanged from the background loader, and the tensor-free
+    job list is the reference's loop order (fit.py:54-65)."""
+    from nerf_attention.fit import enumerate_job_specs, enumerate_jobs, load_layers_async
+    blobs = {l: {'keys': torch.randn(2, 24, 8), 'values': torch.randn(2, 24, 8)} for l in (0, 2)}
+    for l, blob in blobs.items():
+        torch.save(blob, tmp_path / f'layer_{l:02d}.pt')
+    loaded = {l: f.result() for l, f in load_layers_async(tmp_path, [0, 2], pin=False).items()}
+    for l in blobs:
+        assert torch.equal(loaded[l]['keys'], blobs[l]['keys']) and torch.equal(loaded[l]['values'], blobs[l]['values'])
+    assert load_layers_async(tmp_path, [], pin=False) == {}
+    specs = enumerate_job_specs([0, 2], 2, na.CONFIGS_QUICK)
+    jobs = enumerate_jobs(loaded, [0, 1, 2], 2, na.CONFIGS_QUICK)           # layer 1 has no file: skipped
+    assert [j['name'] for j in specs] == [j['name'] for j in jobs]
+    assert specs[0]['name'] == 'L0_H0_key_small' and specs[1]['name'] == 'L0_H0_key_medium'
+    assert specs[2]['name'] == 'L0_H0_value_small' and specs[-1]['name'] == 'L2_H1_value_medium'
+    assert all(s['tensor'] is None for s in specs)
+    assert torch.equal(jobs[2]['tensor'], blobs[0]['values'][0]) and torch.equal(jobs[-1]['tensor'], blobs[2]['values'][1])
