@@ -20,10 +20,11 @@
 // per-CTA scratch that the same thread reads back in the backward half.
 //
 // Roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 4..19 epilogue.  For
-// H <= 256 two tiles ("slots") are in flight per CTA, each owned by its own set of 8 epilogue
-// warps: while one set runs its sine epilogue the tensor core runs the other slot's MMAs, and
-// with 4 epilogue warps per scheduler the TMEM / shared / L2 latencies of one warp hide under
-// the others (the first version alternated 8 warps over both slots and issued 28% of cycles).
+// H <= 256 two tiles ("slots") are in flight per CTA and all 16 epilogue warps take them in turn, step by
+// step: while they run one slot's epilogue the tensor core runs the other slot's MMAs and the store warp
+// writes its operand buffer out, and with 4 epilogue warps per scheduler the TMEM / shared / L2 latencies
+// of one warp hide under the others.  (Earlier versions: 8 warps alternating over both slots issued 28 % of
+// cycles; one set of 8 warps per slot left each set waiting a third of the time for its own MMA.)
 // TMEM: 2 x 256 accumulator columns.  H = 512 needs the whole TMEM and 128 KB of shared memory
 // for one tile: one slot, all 16 warps on it (a quarter of the columns each).
 #pragma once
@@ -48,7 +49,7 @@ template <int H, int NS> struct Cfg {
     static constexpr int BN = (H >= 256) ? 256 : H;              // N of one hidden-layer MMA
     static constexpr int NPARTS = H / BN;
     static constexpr int NSLOT = NS;
-    static constexpr int EPW = NEPI / NSLOT;                      // epilogue warps per slot
+    static constexpr int EPW = NEPI;                              // all epilogue warps work on one slot at a time (alternating)
     static constexpr int CG = EPW / 4;                            // column groups per slot
     static constexpr int CW = H / CG;                             // columns per thread in a hidden step
     static constexpr int NU = CW / 16;                            // 16-column units per thread
@@ -86,7 +87,7 @@ inline bool shape_supported(int N, int D, int H, int L) {
     return N >= 1 && (H == 64 || H == 128 || H == 256 || H == 512) && (D == 64 || D == 128 || D == 256) && L >= 1;
 }
 inline int slots_for(int H);
-inline int loss_partials_per_fit(int N, int H) { return ceil_div(N, BM) * (NEPI / slots_for(H)); }   // one per epilogue warp of the tile
+inline int loss_partials_per_fit(int N, int /*H*/) { return ceil_div(N, BM) * NEPI; }   // one per epilogue warp of the tile
 
 __device__ __forceinline__ void st_shared_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -451,10 +452,11 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        // ===================================================== epilogue warps: one set per slot
-        const int e = warp - NCTRL;
-        const int slot = e / C::EPW;                  // the slot this warp's set owns
-        const int ei = e % C::EPW;
+        // ===================================================== epilogue warps
+        // All 16 warps take the two slots in turn, step by step: (s, slot 0), (s, slot 1), (s+1, slot 0), ..  While they
+        // are busy with one slot the tensor core contracts what they just wrote for the other one, so an MMA (and the
+        // TMA store of its operand) is hidden behind half a step of epilogue work instead of stalling half the warps.
+        const int ei = warp - NCTRL;
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int cg = ei >> 2;                       // column group inside the slot
         const int r = q * 32 + lane;                  // row inside the tile
@@ -463,13 +465,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         const int col0 = cg * C::CW;
         const uint64_t pol_keep = policy_evict_last();
         const bool mufu_hidden = (g.sincos_mode & 1) != 0, mufu_l0 = (g.sincos_mode & 2) != 0;
-        const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
-        const uint32_t t_row = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + col0;
         // cos scratch of one layer: [H/16 units][128 rows][16 columns], so that the 32 lanes of a warp (consecutive
         // rows, 32 B each) touch 1 KB of contiguous memory per access instead of 32 lines at row stride
         constexpr int SCR_U = BM * 16;                // elements between consecutive 16-column units
-        __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H) + (size_t)(col0 / 16) * SCR_U + r * 16;
-        uint32_t acc_phase = 0, free_phase = 0;
+        uint32_t acc_phase = 0, free_phase = 0;       // bit `slot` = parity of acc_full[slot] / buf_free[slot]
 #ifdef NA_CHAIN_TIMING
         long long t_acc = 0, t_kind[4] = {0, 0, 0, 0}, t_begin = clock64(), tq = 0, ts = 0, t_acc0 = 0;
 #define NA_T0() tq = clock64()
@@ -479,15 +478,27 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #define NA_T1()
 #endif
         for (int round = 0;; ++round) {
-            const int tile = tile_of(round, slot);
-            if (tile >= total_tiles) break;
-            const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
-            const FitRec* rec = &g.recs[fit];
-            const int row = mt * BM + r;
-            const bool row_ok = row < g.N;                 // ragged last tile
-            const int row_c = row_ok ? row : g.N - 1;      // a valid row to read inputs from
-            const float omega = rec->omega;
+            // the tiles of this round (per slot), resolved once: the step bodies below run 2 x nsteps times per round
+            const int tile0 = tile_of(round, 0), tile1 = (NSLOT > 1) ? tile_of(round, 1) : total_tiles;
+            if (tile0 >= total_tiles) break;
+            const bool two = tile1 < total_tiles;
+            const int fit0 = tile0 / g.mtiles, mt0 = tile0 - fit0 * g.mtiles;
+            const int fit1 = two ? tile1 / g.mtiles : fit0, mt1 = two ? tile1 - fit1 * g.mtiles : mt0;
+            const float omega0 = g.recs[fit0].omega, omega1 = g.recs[fit1].omega;
             for (int s = 0; s < nsteps; ++s) {
+#pragma unroll 1
+            for (int slot = 0; slot < NSLOT; ++slot) {
+                if (slot == 1 && !two) break;
+                const int fit = slot ? fit1 : fit0, mt = slot ? mt1 : mt0;
+                const FitRec* rec = &g.recs[fit];
+                const int row = mt * BM + r;
+                const bool row_ok = row < g.N;                 // ragged last tile
+                const int row_c = row_ok ? row : g.N - 1;      // a valid row to read inputs from
+                const float omega = slot ? omega1 : omega0;
+                const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
+                const uint32_t t_row = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + col0;
+                __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H)
+                                           + (size_t)(col0 / 16) * SCR_U + r * 16;
 #ifdef NA_CHAIN_TIMING
                 ts = clock64(); t_acc0 = t_acc;
 #endif
@@ -495,8 +506,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     // the buffer is free once the MMA warp has stored the previous tile's dz_0
                     if (!FWD && round > 0) {
                         NA_T0();
-                        mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;       // the MMA warp has seen the last step
-                        mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1;     // the store warp has stored dz_0
+                        mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;       // the MMA warp has seen the last step
+                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;     // the store warp has stored dz_0
                         NA_T1();
                     }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
@@ -537,8 +548,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     float4 bn[4];                                // bias of the next 16 columns (L1-resident)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc) + j);
-                    NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
-                    if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
+                    NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                    if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
                     NA_T1();
                     tc_fence_after();
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
@@ -626,8 +637,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     uint32_t ta[16], tb[16];                     // targets of this unit and the next: two units in flight
                     ld_global_nc_na_256(tn, &ta[0]); ld_global_nc_na_256(tn + 8, &ta[8]);
                     if (nuo > 1) { ld_global_nc_na_256(tn + 16, &tb[0]); ld_global_nc_na_256(tn + 24, &tb[8]); }
-                    NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
-                    if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
+                    NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                    if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
                     NA_T1();
                     tc_fence_after();
                     const uint32_t t_out = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + ocol0;
@@ -666,8 +677,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     uint32_t cc[PFD][8];
 #pragma unroll
                     for (int p = 0; p < PFD; ++p) ld_global_256_hint(csrc + p * SCR_U, cc[p], pol_keep);
-                    NA_T0(); mbar_wait(&acc_full[slot], acc_phase); acc_phase ^= 1;
-                    if (!FWD) { mbar_wait(&buf_free[slot], free_phase); free_phase ^= 1; }
+                    NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                    if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
                     NA_T1();
                     tc_fence_after();
                     uint32_t va[16], vb[16];
@@ -702,11 +713,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     if (CL == 2) mbar_arrive_cluster(&mma_ready[slot], 0);     // the pair's MMA is issued by the leader CTA
                 }
             }
+            }
         }
 #ifdef NA_CHAIN_TIMING
         if (lane == 0 && (ei == 0 || ei == 5) && (blockIdx.x == 0 || blockIdx.x == 77))
-            printf("chain timing cta %d slot %d warp %d: total %lld wait_acc %lld E0 %lld sine %lld out %lld dx %lld\n", (int)blockIdx.x,
-                   slot, ei, clock64() - t_begin, t_acc, t_kind[0], t_kind[1], t_kind[2], t_kind[3]);
+            printf("chain timing cta %d warp %d: total %lld wait_acc %lld E0 %lld sine %lld out %lld dx %lld\n", (int)blockIdx.x,
+                   ei, clock64() - t_begin, t_acc, t_kind[0], t_kind[1], t_kind[2], t_kind[3]);
 #endif
     }
 
@@ -884,7 +896,7 @@ inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const F
 }
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).
-inline int decode_parts(int H) { return slots_for(H) == 2 ? 2 : 4; }
+inline int decode_parts(int /*H*/) { return NEPI / 4; }      // column groups (Cfg::CG)
 inline int build_fwd_maps(int /*N*/, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16, ChainMaps& m) {
     int rc;
     for (int l = 1; l <= L; ++l)
