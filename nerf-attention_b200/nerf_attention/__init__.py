@@ -1,17 +1,20 @@
 """B200-native drop-in for the SIREN fit / reconstruction path of ruskaruma/nerf-attention.
 
 Same import surface as the reference package for everything on that path
-(reference nerf_attention/__init__.py:1-21); analysis and plotting entry points
-of the reference are out of scope and are not re-exported.
+(reference nerf_attention/__init__.py:1-21), including the structure analysis (batched torch
+operations, no figures); plotting entry points are not part of this build.
 """
 
 from nerf_attention.types import (
     CONFIGS_FULL,
     CONFIGS_QUICK,
+    AnalysisResult,
     FitResult,
     KVMetadata,
+    LayerSummary,
     SIRENConfig,
 )
+from nerf_attention.analyze import analyze_kv_cache
 from nerf_attention.siren import SIREN, SineLayer, fit_siren
 from nerf_attention.batched import FitJob, fit_many
 from nerf_attention.extract import extract_kv_cache, extract_kv_cache_synthetic
@@ -25,7 +28,8 @@ from nerf_attention.evaluate import (
 )
 
 __all__ = [
-    'CONFIGS_FULL', 'CONFIGS_QUICK', 'FitResult', 'KVMetadata', 'SIRENConfig',
+    'CONFIGS_FULL', 'CONFIGS_QUICK', 'AnalysisResult', 'FitResult', 'KVMetadata', 'LayerSummary', 'SIRENConfig',
+    'analyze_kv_cache',
     'SIREN', 'SineLayer', 'fit_siren', 'FitJob', 'fit_many',
     'extract_kv_cache', 'extract_kv_cache_synthetic', 'fit_kv_cache',
     'load_results', 'per_position_cosine', 'plot_per_position_error', 'profile_decode',

@@ -1,0 +1,189 @@
+"""KV-cache structure analysis: lag autocorrelation, spectral concentration and effective rank per
+(layer, head), separately for keys and values (reference nerf_attention/analyze.py).
+
+Same entry point, printed report and ``analysis_results.json`` as the reference; what changed is that a tensor
+is analysed in one batched pass of torch operations on ``device`` (all sampled dimensions at once, float64)
+instead of per-dimension numpy loops on the CPU, and that no figure is drawn (matplotlib is not part of this
+build).  This is library code (torch.fft / torch.linalg), not a hand-written kernel: it completes the pipeline
+around the hot path.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from nerf_attention.types import AnalysisResult, KVMetadata, LayerSummary
+
+_PCTS = (0.05, 0.10, 0.25, 0.50)
+
+
+def _default_device(device) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    return torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+
+
+def _autocorrelation(signals: torch.Tensor, max_lag: int = 50) -> torch.Tensor:
+    """[n, k] float64 -> [max_lag + 1, k]: sum(x[:n-lag] * x[lag:]) / sum(x^2) of the centred columns
+    (reference analyze.py:20-30); constant columns give zeros."""
+    n = signals.shape[0]
+    x = signals - signals.mean(dim=0, keepdim=True)
+    var = (x * x).sum(dim=0)
+    out = torch.zeros(max_lag + 1, x.shape[1], dtype=x.dtype, device=x.device)
+    for lag in range(min(max_lag + 1, n)):
+        out[lag] = (x[:n - lag] * x[lag:]).sum(dim=0) / var.clamp_min(1e-300)
+    return torch.where(var < 1e-10, torch.zeros_like(out), out)
+
+
+def _spectral_energy(signals: torch.Tensor) -> dict[str, torch.Tensor]:
+    """Fraction of the Hann-windowed spectrum's energy in the lowest 5/10/25/50 % of the frequencies, per column
+    (reference analyze.py:33-45)."""
+    n = signals.shape[0]
+    window = torch.hann_window(n, periodic=False, dtype=signals.dtype, device=signals.device)   # == np.hanning(n)
+    if n == 1:
+        window = torch.ones(1, dtype=signals.dtype, device=signals.device)
+    windowed = (signals - signals.mean(dim=0, keepdim=True)) * window[:, None]
+    power = torch.fft.rfft(windowed, dim=0).abs() ** 2
+    total = power.sum(dim=0)
+    n_freqs = power.shape[0]
+    out = {}
+    for pct in _PCTS:
+        frac = power[:max(1, int(n_freqs * pct))].sum(dim=0) / total.clamp_min(1e-300)
+        out[f'top_{int(pct * 100)}pct'] = torch.where(total < 1e-10, torch.ones_like(frac), frac)
+    return out
+
+
+def _effective_rank(matrix: torch.Tensor, threshold: float = 0.99) -> dict[str, float]:
+    """Reference analyze.py:48-58."""
+    S = torch.linalg.svdvals(matrix)
+    total = S.sum()
+    rank = int((torch.cumsum(S, dim=0) < threshold * total).sum().item()) + 1
+    return {
+        'effective_rank_99': rank,
+        'full_rank': len(S),
+        'rank_ratio': rank / len(S),
+        'top_sv_fraction': (S[0] / total).item(),
+        'top_10_sv_fraction': (S[:10].sum() / total).item() if len(S) >= 10 else 1.0,
+    }
+
+
+def analyze_tensor(tensor: torch.Tensor, name: str, max_lag: int = 50, device=None) -> dict:
+    """One [seq_len, d_head] tensor (reference ``_analyze_tensor``, analyze.py:61-80)."""
+    dev = _default_device(device)
+    seq_len, d_head = tensor.shape
+    dims_to_sample = min(d_head, 16)
+    dim_indices = list(range(0, d_head, max(1, d_head // dims_to_sample)))
+    full = tensor.detach().to(dev, torch.float64)
+    sampled = full[:, dim_indices]
+    mean_autocorr = _autocorrelation(sampled, max_lag).mean(dim=1)
+    energy = {k: float(v.mean().item()) for k, v in _spectral_energy(sampled).items()}
+    return {
+        'name': name,
+        'shape': list(tensor.shape),
+        'lag1_autocorrelation': float(mean_autocorr[1].item()) if len(mean_autocorr) > 1 else 0.0,
+        'mean_autocorrelation': mean_autocorr.tolist(),
+        'spectral_energy': energy,
+        'rank': _effective_rank(full),
+    }
+
+
+def _select_layers(num_layers: int) -> list[int]:
+    return sorted({0, num_layers // 4, num_layers // 2, 3 * num_layers // 4, num_layers - 1})
+
+
+def _feasibility_label(val: float, good: float = 0.5, bad: float = 0.2) -> str:
+    return 'GOOD' if val > good else 'CONCERNING' if val > bad else 'BAD'
+
+
+def analyze_kv_cache(kv_dir: Path, output_dir: Path, device=None) -> AnalysisResult:
+    """Structure analysis across sampled layers and heads (reference analyze.py:96-216)."""
+    kv_dir, output_dir = Path(kv_dir), Path(output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    with open(kv_dir / 'metadata.json') as f:
+        metadata = KVMetadata.from_dict(json.load(f))
+    print(f"Analyzing KV cache: {metadata.num_layers} layers x {metadata.num_kv_heads} heads")
+    print(f"Sequence length: {metadata.seq_len}, Head dim: {metadata.head_dim}")
+
+    all_results: list[dict] = []
+    layer_summaries: list[LayerSummary] = []
+    for layer_idx in _select_layers(metadata.num_layers):
+        filepath = kv_dir / f'layer_{layer_idx:02d}.pt'
+        if not filepath.exists():
+            print(f"  Skipping layer {layer_idx} (not found)")
+            continue
+        data = torch.load(filepath, map_location='cpu', weights_only=True)
+        stats = {'k': ([], [], []), 'v': ([], [], [])}
+        for head_idx in range(min(metadata.num_kv_heads, 4)):
+            for tag, tensor in (('k', data['keys'][head_idx]), ('v', data['values'][head_idx])):
+                res = analyze_tensor(tensor, f'L{layer_idx}_H{head_idx}_{tag.upper()}', device=device)
+                all_results.append(res)
+                ac, en, rk = stats[tag]
+                ac.append(res['lag1_autocorrelation'])
+                en.append(res['spectral_energy']['top_10pct'])
+                rk.append(res['rank']['rank_ratio'])
+        summary = LayerSummary(
+            layer=layer_idx,
+            avg_autocorr_k=float(np.mean(stats['k'][0])), avg_autocorr_v=float(np.mean(stats['v'][0])),
+            avg_energy_10pct_k=float(np.mean(stats['k'][1])), avg_energy_10pct_v=float(np.mean(stats['v'][1])),
+            avg_rank_ratio_k=float(np.mean(stats['k'][2])), avg_rank_ratio_v=float(np.mean(stats['v'][2])),
+        )
+        layer_summaries.append(summary)
+        print(f"\n  Layer {layer_idx}:")
+        print(f"    Keys   - Autocorr: {summary.avg_autocorr_k:.3f} | Spectral: {summary.avg_energy_10pct_k:.3f} | "
+              f"Rank: {summary.avg_rank_ratio_k:.3f}")
+        print(f"    Values - Autocorr: {summary.avg_autocorr_v:.3f} | Spectral: {summary.avg_energy_10pct_v:.3f} | "
+              f"Rank: {summary.avg_rank_ratio_v:.3f}")
+
+    avg_ac_k = float(np.mean([s.avg_autocorr_k for s in layer_summaries]))
+    avg_ac_v = float(np.mean([s.avg_autocorr_v for s in layer_summaries]))
+    avg_en_k = float(np.mean([s.avg_energy_10pct_k for s in layer_summaries]))
+    avg_en_v = float(np.mean([s.avg_energy_10pct_v for s in layer_summaries]))
+
+    print(f"\n{'=' * 60}\nSIREN FEASIBILITY ASSESSMENT\n{'=' * 60}")
+    print("\nAutocorrelation (lag-1):")
+    print(f"  Keys:   {avg_ac_k:.3f}  {_feasibility_label(avg_ac_k)} (>0.5)")
+    print(f"  Values: {avg_ac_v:.3f}  {_feasibility_label(avg_ac_v)} (>0.5)")
+    print("\nSpectral concentration (energy in lowest 10% frequencies):")
+    print(f"  Keys:   {avg_en_k:.3f}  {_feasibility_label(avg_en_k)} (>0.5)")
+    print(f"  Values: {avg_en_v:.3f}  {_feasibility_label(avg_en_v)} (>0.5)")
+    print("\nOverall prediction:")
+    if avg_ac_k > 0.5 and avg_en_k > 0.5:
+        print("  PROMISING: KV cache has significant structure. SIREN should compress well.")
+    elif avg_ac_k > 0.2 or avg_en_k > 0.3:
+        print("  MIXED: Some structure. SIREN may work partially.")
+    else:
+        print("  CHALLENGING: Noisy/unstructured. Document why it fails.")
+
+    result = AnalysisResult(metadata=metadata, layer_summaries=layer_summaries, avg_autocorr_keys=avg_ac_k,
+                            avg_autocorr_values=avg_ac_v, avg_spectral_keys=avg_en_k, avg_spectral_values=avg_en_v)
+    results_data = {
+        'metadata': metadata.to_dict(),
+        'layer_summaries': [{k: getattr(s, k) for k in ('layer', 'avg_autocorr_k', 'avg_autocorr_v',
+                                                        'avg_energy_10pct_k', 'avg_energy_10pct_v',
+                                                        'avg_rank_ratio_k', 'avg_rank_ratio_v')}
+                            for s in layer_summaries],
+        'assessment': {'avg_autocorr_keys': avg_ac_k, 'avg_autocorr_values': avg_ac_v,
+                       'avg_spectral_keys': avg_en_k, 'avg_spectral_values': avg_en_v},
+    }
+    with open(output_dir / 'analysis_results.json', 'w') as f:
+        json.dump(results_data, f, indent=2)
+    print(f"\nResults saved to {output_dir}/")
+    return result
+
+
+def main() -> None:
+    parser = argparse.ArgumentParser(description='Analyze KV cache structure')
+    parser.add_argument('--kv_dir', type=str, default='results/kv_cache')
+    parser.add_argument('--output_dir', type=str, default='results/analysis')
+    parser.add_argument('--device', type=str, default=None)
+    args = parser.parse_args()
+    analyze_kv_cache(Path(args.kv_dir), Path(args.output_dir), device=args.device)
+
+
+if __name__ == '__main__':
+    main()

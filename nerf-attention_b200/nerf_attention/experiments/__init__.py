@@ -6,5 +6,6 @@ from nerf_attention.experiments.scaling import (
     run_full_layer_profile,
     run_scaling_experiment,
 )
+from nerf_attention.experiments.svd import run_svd_experiment
 
-__all__ = ['run_scaling_experiment', 'run_full_layer_profile', 'crossover_data']
+__all__ = ['run_scaling_experiment', 'run_full_layer_profile', 'crossover_data', 'run_svd_experiment']

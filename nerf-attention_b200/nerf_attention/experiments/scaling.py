@@ -12,8 +12,8 @@ follow from the batched B200 path:
   ``hbm_b200_measured_ms`` / ``siren_decode_qk_ms`` come from the real kernels, batched over
   ``heads_per_launch`` heads because one head is far below launch latency;
 * real-model extraction is out of scope: ``model_name='synthetic'`` uses the
-  reference's synthetic generator; the structure-analysis columns (``autocorr_*``,
-  ``spectral_*``, reference analyze.py, out of scope) are written as ``None``.
+  reference's synthetic generator.  The structure-analysis columns (``autocorr_*``, ``spectral_*``,
+  scaling.py:153-157,202-205) come from ``nerf_attention.analyze.analyze_kv_cache`` on the device.
 """
 
 from __future__ import annotations
@@ -27,6 +27,7 @@ import torch
 from nerf_attention import _native
 from nerf_attention.batched import FitJob, fit_many
 from nerf_attention.evaluate import PackedModels, _load_model_from_checkpoint, _time_cuda, kvread_qk
+from nerf_attention.analyze import _select_layers, analyze_kv_cache
 from nerf_attention.extract import extract_kv_cache_synthetic
 from nerf_attention.types import KVMetadata, SIRENConfig
 
@@ -104,7 +105,8 @@ def run_scaling_experiment(
     base_dir.mkdir(parents=True, exist_ok=True)
     layers = sorted({0, num_layers // 2, num_layers - 1})              # scaling.py:160
 
-    # Phase 1: KV tensors of every length (only the layers that are fitted are written)
+    # Phase 1: KV tensors of every length (only the layers that are fitted or analysed are written)
+    written = sorted(set(layers) | set(_select_layers(num_layers)))
     metadata_map: dict[int, KVMetadata] = {}
     for seq_len in seq_lengths:
         kv_dir = base_dir / f'seq_{seq_len}' / 'kv_cache'
@@ -112,7 +114,7 @@ def run_scaling_experiment(
             metadata_map[seq_len] = KVMetadata.from_dict(json.loads((kv_dir / 'metadata.json').read_text()))
         else:
             metadata_map[seq_len] = extract_kv_cache_synthetic(seq_len, num_layers, num_kv_heads, head_dim, kv_dir,
-                                                               layers=layers)
+                                                               layers=written)
 
     # Phase 2: every medium fit of the experiment in one batched call
     jobs, where = [], []
@@ -143,13 +145,16 @@ def run_scaling_experiment(
             print(f'  seq {seq_len} {name}: CosSim={result.final_cosine_mean:.4f}, '
                   f'Compress={result.compression_ratio:.1f}x')
         siren_time_ms = _profile_siren_latency(fits_dir, metadata.seq_len, device)
+        analysis = analyze_kv_cache(base_dir / f'seq_{seq_len}' / 'kv_cache', base_dir / f'seq_{seq_len}' / 'analysis',
+                                    device=device)
         raw_bytes = metadata.seq_len * metadata.head_dim * 2            # KV cache is float16
         key_r = [r for r in fit_results if r['kv_type'] == 'key']
         val_r = [r for r in fit_results if r['kv_type'] == 'value']
         row = {
             'seq_len': metadata.seq_len,
             'actual_tokens': metadata.actual_tokens,
-            'autocorr_keys': None, 'autocorr_values': None, 'spectral_keys': None, 'spectral_values': None,
+            'autocorr_keys': analysis.avg_autocorr_keys, 'autocorr_values': analysis.avg_autocorr_values,
+            'spectral_keys': analysis.avg_spectral_keys, 'spectral_values': analysis.avg_spectral_values,
             'avg_cossim_keys': float(np.mean([r['final_cosine_mean'] for r in key_r])) if key_r else 0.0,
             'avg_cossim_values': float(np.mean([r['final_cosine_mean'] for r in val_r])) if val_r else 0.0,
             'avg_compression': float(np.mean([r['compression_ratio'] for r in fit_results])),

@@ -109,6 +109,9 @@ def test_scaling_experiment_and_layer_profile_outputs(cuda_device, tmp_path):
         assert r['hbm_4060_ms'] == pytest.approx(n * 128 * 2 / 272e9 * 1000)
         assert r['hbm_b200_measured_ms'] > 0 and r['siren_decode_qk_ms'] > 0
         assert 0.0 < r['avg_cossim_keys'] <= 1.0
+        assert 0.5 < r['autocorr_keys'] < 1.0 and 0.5 < r['autocorr_values'] < 1.0       # synthetic KV is smooth (analyze.py)
+        assert 0.0 < r['spectral_keys'] <= 1.0 and 0.0 < r['spectral_values'] <= 1.0
+        assert (tmp_path / 'scaling' / f'seq_{n}' / 'analysis' / 'analysis_results.json').exists()
         assert len(list((tmp_path / 'scaling' / f'seq_{n}' / 'fits').glob('*_model.pt'))) == 6
     ckpt = torch.load(tmp_path / 'scaling' / 'seq_256' / 'fits' / 'L0_H0_key_medium_model.pt', weights_only=True)
     assert sorted(ckpt) == ['config', 'metrics', 'model_state', 'target_mean', 'target_std']   # scaling.py:175-187
