@@ -204,6 +204,9 @@ __device__ __forceinline__ Step step_info(int s, int L, int D) {
     return st;
 }
 
+#ifndef NA_RECOMPUTE_COS0
+#define NA_RECOMPUTE_COS0 1
+#endif
 template <bool MUFU>
 __device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], float (&c)[8]) {
     if (MUFU) sincos_group_mufu(x, s, c); else sincos_group(x, s, c);
@@ -465,6 +468,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         const int col0 = cg * C::CW;
         const uint64_t pol_keep = policy_evict_last();
         const bool mufu_hidden = (g.sincos_mode & 1) != 0, mufu_l0 = (g.sincos_mode & 2) != 0;
+        // cos of layer 0 is recomputed in the last backward step from the position and the prescaled W0 / b0 (one FFMA,
+        // a reduction and one MUFU per element) instead of being parked in the scratch: a third of the scratch traffic
+        // (and its DRAM spill) for the price of SFU work moved from the longest step into the shortest
+        constexpr bool recompute_cos0 = !FWD && NA_RECOMPUTE_COS0;
         // cos scratch of one layer: [H/16 units][128 rows][16 columns], so that the 32 lanes of a warp (consecutive
         // rows, 32 B each) touch 1 KB of contiguous memory per access instead of 32 lines at row stride
         constexpr int SCR_U = BM * 16;                // elements between consecutive 16-column units
@@ -540,7 +547,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             }
                         }
                         act_store16(act_u32, r, col0 + u * 16, so);
-                        if (!FWD) st_global_256_hint(scr + u * SCR_U, co, pol_keep);
+                        if (!FWD && !recompute_cos0) st_global_256_hint(scr + u * SCR_U, co, pol_keep);
                     }
                 } else if (s <= L) {
                     // ---------------- hidden sine layer s
@@ -673,6 +680,44 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 } else {
                     // ---------------- backward: dz_{lp} = (dz_{lp+1} W_{lp+1}) * w cos_{lp}
                     const int lp = 2 * L + 2 - s;                // L, L-1, .., 0
+                    if (lp == 0 && recompute_cos0) {
+                        const float x = __ldg(rec->pos + row_c);
+                        const float* w0 = g.psc + (size_t)fit * g.psc_fit + col0;
+                        const float* b0 = g.psc + (size_t)fit * g.psc_fit + H + col0;
+                        NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;
+                        NA_T1();
+                        tc_fence_after();
+                        uint32_t v[16];
+                        tmem_ld16(t_row, v);
+#pragma unroll 1
+                        for (int u = 0; u < NU; ++u) {
+                            float cs[16];
+#pragma unroll
+                            for (int gi = 0; gi < 2; ++gi) {         // the same arguments and sin/cos routine as layer 0 (s == 0)
+                                const float4* wp = reinterpret_cast<const float4*>(w0 + u * 16 + gi * 8);
+                                const float4* bp = reinterpret_cast<const float4*>(b0 + u * 16 + gi * 8);
+                                float arg[8], sn[8], c8[8];
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const float4 wv = __ldg(wp + j), bv = __ldg(bp + j);
+                                    arg[4 * j] = fmaf(x, wv.x, bv.x); arg[4 * j + 1] = fmaf(x, wv.y, bv.y);
+                                    arg[4 * j + 2] = fmaf(x, wv.z, bv.z); arg[4 * j + 3] = fmaf(x, wv.w, bv.w);
+                                }
+                                if (mufu_l0) sincos8<true>(arg, sn, c8); else sincos8<false>(arg, sn, c8);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) cs[gi * 8 + j] = c8[j];
+                            }
+                            tmem_ld_wait();
+                            uint32_t dout[8];
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * cs[2 * t]),
+                                                    __uint_as_float(v[2 * t + 1]) * (omega * cs[2 * t + 1]));
+                            if (u + 1 < NU) tmem_ld16(t_row + (u + 1) * 16, v);
+                            act_store16(act_u32, r, col0 + u * 16, dout);
+                        }
+                    } else {
                     const __nv_bfloat16* csrc = scr + (size_t)lp * (BM * H);
                     uint32_t cc[PFD][8];
 #pragma unroll
@@ -698,6 +743,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         }
                         if (u + PFD < NU) ld_global_256_hint(csrc + (u + PFD) * SCR_U, cc[u % PFD], pol_keep);
                         act_store16(act_u32, r, col0 + u * 16, dout);
+                    }
                     }
                 }
                 // operand buffer complete: hand it to the MMA warp (stores it to global, then contracts it)
