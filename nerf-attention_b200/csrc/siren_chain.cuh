@@ -66,7 +66,7 @@ struct ChainArgs {
     int N, D, L, nf, mtiles;
     const FitRec* recs;
     int w_off[kMaxLayers], b_off[kMaxLayers];
-    __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][H/16][128][16]
+    __nv_bfloat16* scratch;                 // cos_l of the tiles in flight: [grid][NSLOT][L+1][H/16][128][16] (slot 0 of L+1 unused: cos_0 is recomputed)
     float* losspart; int losspart_per_fit; float loss_scale;
     const float* dotvec; float* dotpart;    // forward-only (decode): u [nf][H] fp32, partial scores [nf][CG][N]
     const float* pvec; float* pvpart;       // forward-only (decode, values): p [nf][N] fp32, partial sums [nf][N/32][H]
