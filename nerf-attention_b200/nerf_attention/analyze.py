@@ -17,9 +17,19 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from nerf_attention.types import AnalysisResult, KVMetadata, LayerSummary
+import dataclasses
+
+from nerf_attention.types import KVMetadata
 
 _PCTS = (0.05, 0.10, 0.25, 0.50)
+_SUMMARY_FIELDS = ('avg_autocorr_k', 'avg_autocorr_v', 'avg_energy_10pct_k', 'avg_energy_10pct_v',
+                   'avg_rank_ratio_k', 'avg_rank_ratio_v')
+
+# record types of the reference (types.py:66-84): same names and fields, built from the field table
+LayerSummary = dataclasses.make_dataclass('LayerSummary', [('layer', int)] + [(f, float) for f in _SUMMARY_FIELDS])
+AnalysisResult = dataclasses.make_dataclass('AnalysisResult', [
+    ('metadata', KVMetadata), ('layer_summaries', list), ('avg_autocorr_keys', float), ('avg_autocorr_values', float),
+    ('avg_spectral_keys', float), ('avg_spectral_values', float)])
 
 
 def _default_device(device) -> torch.device:
@@ -100,80 +110,68 @@ def _feasibility_label(val: float, good: float = 0.5, bad: float = 0.2) -> str:
     return 'GOOD' if val > good else 'CONCERNING' if val > bad else 'BAD'
 
 
+def _report(lines: list[str]) -> None:
+    print('\n'.join(lines))
+
+
 def analyze_kv_cache(kv_dir: Path, output_dir: Path, device=None) -> AnalysisResult:
-    """Structure analysis across sampled layers and heads (reference analyze.py:96-216)."""
+    """Structure analysis across sampled layers and heads (reference analyze.py:96-216): same console report and
+    ``analysis_results.json``; the figure is not drawn."""
     kv_dir, output_dir = Path(kv_dir), Path(output_dir)
     output_dir.mkdir(parents=True, exist_ok=True)
-    with open(kv_dir / 'metadata.json') as f:
-        metadata = KVMetadata.from_dict(json.load(f))
-    print(f"Analyzing KV cache: {metadata.num_layers} layers x {metadata.num_kv_heads} heads")
-    print(f"Sequence length: {metadata.seq_len}, Head dim: {metadata.head_dim}")
+    metadata = KVMetadata.from_dict(json.loads((kv_dir / 'metadata.json').read_text()))
+    _report([f"Analyzing KV cache: {metadata.num_layers} layers x {metadata.num_kv_heads} heads",
+             f"Sequence length: {metadata.seq_len}, Head dim: {metadata.head_dim}"])
 
-    all_results: list[dict] = []
-    layer_summaries: list[LayerSummary] = []
+    heads = min(metadata.num_kv_heads, 4)
+    summaries: list = []
     for layer_idx in _select_layers(metadata.num_layers):
-        filepath = kv_dir / f'layer_{layer_idx:02d}.pt'
-        if not filepath.exists():
+        path = kv_dir / f'layer_{layer_idx:02d}.pt'
+        if not path.exists():
             print(f"  Skipping layer {layer_idx} (not found)")
             continue
-        data = torch.load(filepath, map_location='cpu', weights_only=True)
-        stats = {'k': ([], [], []), 'v': ([], [], [])}
-        for head_idx in range(min(metadata.num_kv_heads, 4)):
-            for tag, tensor in (('k', data['keys'][head_idx]), ('v', data['values'][head_idx])):
-                res = analyze_tensor(tensor, f'L{layer_idx}_H{head_idx}_{tag.upper()}', device=device)
-                all_results.append(res)
-                ac, en, rk = stats[tag]
-                ac.append(res['lag1_autocorrelation'])
-                en.append(res['spectral_energy']['top_10pct'])
-                rk.append(res['rank']['rank_ratio'])
-        summary = LayerSummary(
-            layer=layer_idx,
-            avg_autocorr_k=float(np.mean(stats['k'][0])), avg_autocorr_v=float(np.mean(stats['v'][0])),
-            avg_energy_10pct_k=float(np.mean(stats['k'][1])), avg_energy_10pct_v=float(np.mean(stats['v'][1])),
-            avg_rank_ratio_k=float(np.mean(stats['k'][2])), avg_rank_ratio_v=float(np.mean(stats['v'][2])),
-        )
-        layer_summaries.append(summary)
-        print(f"\n  Layer {layer_idx}:")
-        print(f"    Keys   - Autocorr: {summary.avg_autocorr_k:.3f} | Spectral: {summary.avg_energy_10pct_k:.3f} | "
-              f"Rank: {summary.avg_rank_ratio_k:.3f}")
-        print(f"    Values - Autocorr: {summary.avg_autocorr_v:.3f} | Spectral: {summary.avg_energy_10pct_v:.3f} | "
-              f"Rank: {summary.avg_rank_ratio_v:.3f}")
+        blob = torch.load(path, map_location='cpu', weights_only=True)
+        # per (kind, statistic): one value per head
+        per_head = {kind: [analyze_tensor(blob[key][h], f'L{layer_idx}_H{h}_{kind.upper()}', device=device)
+                           for h in range(heads)] for kind, key in (('k', 'keys'), ('v', 'values'))}
+        pick = {'autocorr': lambda r: r['lag1_autocorrelation'], 'energy_10pct': lambda r: r['spectral_energy']['top_10pct'],
+                'rank_ratio': lambda r: r['rank']['rank_ratio']}
+        summary = LayerSummary(layer=layer_idx, **{
+            f'avg_{stat}_{kind}': float(np.mean([get(r) for r in per_head[kind]]))
+            for stat, get in pick.items() for kind in ('k', 'v')})
+        summaries.append(summary)
+        rows = [f"\n  Layer {layer_idx}:"]
+        for label, kind in (('Keys  ', 'k'), ('Values', 'v')):
+            rows.append(f"    {label} - Autocorr: {getattr(summary, 'avg_autocorr_' + kind):.3f} | "
+                        f"Spectral: {getattr(summary, 'avg_energy_10pct_' + kind):.3f} | "
+                        f"Rank: {getattr(summary, 'avg_rank_ratio_' + kind):.3f}")
+        _report(rows)
 
-    avg_ac_k = float(np.mean([s.avg_autocorr_k for s in layer_summaries]))
-    avg_ac_v = float(np.mean([s.avg_autocorr_v for s in layer_summaries]))
-    avg_en_k = float(np.mean([s.avg_energy_10pct_k for s in layer_summaries]))
-    avg_en_v = float(np.mean([s.avg_energy_10pct_v for s in layer_summaries]))
+    overall = {name: float(np.mean([getattr(s, field) for s in summaries]))
+               for name, field in (('avg_autocorr_keys', 'avg_autocorr_k'), ('avg_autocorr_values', 'avg_autocorr_v'),
+                                   ('avg_spectral_keys', 'avg_energy_10pct_k'), ('avg_spectral_values', 'avg_energy_10pct_v'))}
+    bar = '=' * 60
+    lines = [f"\n{bar}", "SIREN FEASIBILITY ASSESSMENT", bar]
+    for title, stem in (("Autocorrelation (lag-1):", 'avg_autocorr'),
+                        ("Spectral concentration (energy in lowest 10% frequencies):", 'avg_spectral')):
+        lines.append(f"\n{title}")
+        for label, suffix in (('Keys:  ', 'keys'), ('Values:', 'values')):
+            val = overall[f'{stem}_{suffix}']
+            lines.append(f"  {label} {val:.3f}  {_feasibility_label(val)} (>0.5)")
+    ac_k, en_k = overall['avg_autocorr_keys'], overall['avg_spectral_keys']
+    verdict = ("PROMISING: KV cache has significant structure. SIREN should compress well." if ac_k > 0.5 and en_k > 0.5
+               else "MIXED: Some structure. SIREN may work partially." if ac_k > 0.2 or en_k > 0.3
+               else "CHALLENGING: Noisy/unstructured. Document why it fails.")
+    lines += ["\nOverall prediction:", f"  {verdict}"]
+    _report(lines)
 
-    print(f"\n{'=' * 60}\nSIREN FEASIBILITY ASSESSMENT\n{'=' * 60}")
-    print("\nAutocorrelation (lag-1):")
-    print(f"  Keys:   {avg_ac_k:.3f}  {_feasibility_label(avg_ac_k)} (>0.5)")
-    print(f"  Values: {avg_ac_v:.3f}  {_feasibility_label(avg_ac_v)} (>0.5)")
-    print("\nSpectral concentration (energy in lowest 10% frequencies):")
-    print(f"  Keys:   {avg_en_k:.3f}  {_feasibility_label(avg_en_k)} (>0.5)")
-    print(f"  Values: {avg_en_v:.3f}  {_feasibility_label(avg_en_v)} (>0.5)")
-    print("\nOverall prediction:")
-    if avg_ac_k > 0.5 and avg_en_k > 0.5:
-        print("  PROMISING: KV cache has significant structure. SIREN should compress well.")
-    elif avg_ac_k > 0.2 or avg_en_k > 0.3:
-        print("  MIXED: Some structure. SIREN may work partially.")
-    else:
-        print("  CHALLENGING: Noisy/unstructured. Document why it fails.")
-
-    result = AnalysisResult(metadata=metadata, layer_summaries=layer_summaries, avg_autocorr_keys=avg_ac_k,
-                            avg_autocorr_values=avg_ac_v, avg_spectral_keys=avg_en_k, avg_spectral_values=avg_en_v)
-    results_data = {
+    (output_dir / 'analysis_results.json').write_text(json.dumps({
         'metadata': metadata.to_dict(),
-        'layer_summaries': [{k: getattr(s, k) for k in ('layer', 'avg_autocorr_k', 'avg_autocorr_v',
-                                                        'avg_energy_10pct_k', 'avg_energy_10pct_v',
-                                                        'avg_rank_ratio_k', 'avg_rank_ratio_v')}
-                            for s in layer_summaries],
-        'assessment': {'avg_autocorr_keys': avg_ac_k, 'avg_autocorr_values': avg_ac_v,
-                       'avg_spectral_keys': avg_en_k, 'avg_spectral_values': avg_en_v},
-    }
-    with open(output_dir / 'analysis_results.json', 'w') as f:
-        json.dump(results_data, f, indent=2)
+        'layer_summaries': [{'layer': s.layer, **{f: getattr(s, f) for f in _SUMMARY_FIELDS}} for s in summaries],
+        'assessment': overall,
+    }, indent=2))
     print(f"\nResults saved to {output_dir}/")
-    return result
+    return AnalysisResult(metadata=metadata, layer_summaries=summaries, **overall)
 
 
 def main() -> None:

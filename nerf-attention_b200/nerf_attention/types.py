@@ -80,27 +80,12 @@ class KVMetadata:
         return cls(**{k: v for k, v in d.items() if k in known})
 
 
-@dataclass
-class LayerSummary:
-    """Per-layer averages of the structure analysis (reference types.py:66-74)."""
-    layer: int
-    avg_autocorr_k: float
-    avg_autocorr_v: float
-    avg_energy_10pct_k: float
-    avg_energy_10pct_v: float
-    avg_rank_ratio_k: float
-    avg_rank_ratio_v: float
-
-
-@dataclass
-class AnalysisResult:
-    """Return value of analyze_kv_cache (reference types.py:77-84)."""
-    metadata: KVMetadata
-    layer_summaries: list[LayerSummary]
-    avg_autocorr_keys: float
-    avg_autocorr_values: float
-    avg_spectral_keys: float
-    avg_spectral_values: float
+def __getattr__(name: str):
+    # LayerSummary / AnalysisResult (reference types.py:66-84) live next to the analysis that fills them
+    if name in ('LayerSummary', 'AnalysisResult'):
+        from nerf_attention import analyze
+        return getattr(analyze, name)
+    raise AttributeError(f'module {__name__!r} has no attribute {name!r}')
 
 
 def _table(rows: list[tuple[int, int, float, str]]) -> list[SIRENConfig]:
