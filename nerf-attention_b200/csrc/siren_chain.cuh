@@ -962,9 +962,11 @@ inline int launch_decode(int N, int D, int H, int L, int nf, const LayerMap& lm,
 }
 
 inline int configure_all() {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
+    static std::once_flag once_dev[kMaxDevices];
+    static cudaError_t err_dev[kMaxDevices] = {};
+    const int dev = current_device();
+    cudaError_t& err = err_dev[dev];
+    std::call_once(once_dev[dev], [&err] {
         auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
 #define NA_CHAIN_CFG1(HH, NS, MODE, CL) \
         acc(cudaFuncSetAttribute(chain_kernel<HH, NS, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HH, NS>::SMEM));

@@ -695,10 +695,19 @@ inline int build_group_maps(int N, int D, int H, int L, int nf, const LayerMap& 
 }
 
 // ------------------------------------------------------------------ host: launches
+// Kernel attributes (the dynamic shared-memory opt-in) and the SM count belong to a device, not to the process:
+// both are cached per device ordinal, so a second GPU used from the same process is configured on first use.
+constexpr int kMaxDevices = 64;
+inline int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < kMaxDevices) ? dev : 0; }
 inline int num_sms() {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-    return n;
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!n[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
+    }
+    return n[dev];
 }
 
 // bit m of the mask selects the 2-CTA/SM variant for Mode m (NERFATTN_OCC2 overrides the default)
@@ -802,9 +811,11 @@ inline cudaError_t configure_one() {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN, 2>());
 }
 inline int configure_all() {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
+    static std::once_flag once_dev[kMaxDevices];
+    static cudaError_t err_dev[kMaxDevices] = {};
+    const int dev = current_device();
+    cudaError_t& err = err_dev[dev];
+    std::call_once(once_dev[dev], [&err] {
         auto acc = [&](cudaError_t e) { if (e != cudaSuccess && err == cudaSuccess) err = e; };
 #define NA_CFG3(MODE, A, B) acc(configure_one<MODE, A, B, 64>()); acc(configure_one<MODE, A, B, 128>()); acc(configure_one<MODE, A, B, 256>());
         NA_CFG3(kRaw, false, false) NA_CFG3(kRaw, false, true) NA_CFG3(kRaw, true, false) NA_CFG3(kRaw, true, true)

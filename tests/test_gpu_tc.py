@@ -119,22 +119,6 @@ def test_unsupported_shapes_fail_loudly(cuda_device):
         gpu_fit(smooth_tensor(1, 128, 128), cfg, 1, 'tf32', seeded_state(cfg, 128, 1))
 
 
-@pytest.mark.skipif(not os.environ.get('NERFATTN_LONG'), reason='long run: set NERFATTN_LONG=1')
-@pytest.mark.parametrize('name', ['medium', 'hifreq'])
-def test_full_length_fit_both_modes(cuda_device, name):
-    """BASELINE config 2 in full: 2048x128 keys, 2000 epochs, against the oracle."""
-    from nerf_attention.extract import synthetic_head
-    cfg = next(c for c in na.CONFIGS_FULL if c.name == name)
-    kv, _ = synthetic_head(16, 0, 2048, 32, 8, 128)
-    state = seeded_state(cfg, 128, 16002)
-    ref = oracle_fit(kv, cfg, 2000, state)
-    fp32 = gpu_fit(kv, cfg, 2000, 'fp32', state)
-    bf16 = gpu_fit(kv, cfg, 2000, 'bf16', state)
-    print(f'\n{name}: oracle {ref.final_cosine_mean:.6f} fp32 {fp32.final_cosine_mean:.6f} bf16 {bf16.final_cosine_mean:.6f}')
-    assert abs(fp32.final_cosine_mean - ref.final_cosine_mean) <= 1e-3
-    assert abs(bf16.final_cosine_mean - ref.final_cosine_mean) <= COS_ATOL_BF16
-
-
 @pytest.mark.parametrize('mode,tol', [(0, 1.5e-7), (1, 6e-7)])
 def test_sincos_accuracy(cuda_device, mode, tol):
     """Device sin/cos against float64.  mode 0 (polynomial: fp32 path and layer 0) stays within fp32
