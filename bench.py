@@ -291,7 +291,8 @@ def run_native(args) -> None:
     phases = None
     if rank == 0 and args.precision == 'bf16' and os.environ.get('NERFATTN_NO_CHAIN', '0') in ('', '0'):
         pe = max(20, min(100, args.epochs))
-        pbatch = batched.FitBatch(jobs, epochs=pe, device=str(dev), precision=args.precision, keep_initial=True)
+        pbatch = batched.FitBatch(jobs, epochs=pe, device=str(dev), precision=args.precision, keep_initial=True,
+                                  lib=_native.prof_lib())      # -DNA_PROFILING build: honours NERFATTN_PHASE
 
         def phase_ms(mask: int) -> float:
             os.environ['NERFATTN_PHASE'] = str(mask)

@@ -36,6 +36,8 @@ struct FitRec {
     float* mean_out;        // caller's [D]
     float* std_out;         // caller's [D]
     float omega;
+    int prenorm;            // NA_FIT_TARGETS_PRENORMALISED: traw holds (t - mean) / std
+    int posid;              // index of this fit's position vector among the distinct ones of its group
     int uniq;               // index of the unique target tensor
     int fit_index;          // position in the caller's job list
 };

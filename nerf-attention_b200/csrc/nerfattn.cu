@@ -20,6 +20,7 @@
 #include "siren_fp32.cuh"
 #include "siren_tc.cuh"
 #include "siren_chain.cuh"
+#include "siren_dw.cuh"
 #include "decode.cuh"
 #include "synth.cuh"
 
@@ -60,14 +61,34 @@ struct Group {
     float* xpart;          // [nf][mtiles][H]
     float* losspart; int losspart_per_fit;
     __nv_bfloat16* wbf16;  // [nf][P] bf16 mirror of the weights (tensor path)
-    tc::GroupMaps* maps;   // TMA descriptors (tensor path), host-side
+    tc::GroupMaps* maps;   // TMA descriptors (unfused tensor path), host-side
     // fused row-tile chain (siren_chain.cuh): forward + loss + dX chain in one kernel; cosb[l] then
-    // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch
+    // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch.  The group is trained in
+    // `nchunks` sub-batches of `chunk` fits that share ONE set of activation buffers (act / cosb / dy hold
+    // `chunk` fits): chain(c) -> dW + Adam(c) back to back, so that what the chain kernel stores is still
+    // in L2 when the dW kernel reads it, and the next sub-batch overwrites the same lines.
     bool use_chain;
+    int chunk, nchunks;
     __nv_bfloat16* chain_scratch;
     float* psc;            // omega-prescaled W0 / sine-layer biases [nf][(L+2)H]
-    chain::ChainMaps* cmaps;
+    std::vector<chain::ChainMaps> cmaps;   // per sub-batch (the weight maps start at the sub-batch's first fit)
+    dw::DwMaps dmaps;
+    // layer-0 gradient operand (chain::xop_kernel): one table per distinct position vector of the group
+    std::vector<const float*> pos_tabs; std::vector<int> posid;    // posid[k]: table of the group's k-th fit
+    const float** d_pos_tabs; __nv_bfloat16* xop;
 };
+
+// Fits per sub-batch of a chain group.  NERFATTN_CHUNK_MB (tuning): bf16 activation bytes per sub-batch.
+static int chain_chunk_fits(int N, int D, int H, int L, int nf) {
+    const char* e = getenv("NERFATTN_CHUNK_MB");
+    const double mb = e ? atof(e) : 0.0;
+    if (mb <= 0.0) return nf;
+    const double per_fit = ((double)2 * (L + 1) * N * H + (double)N * D) * 2.0;
+    int c = (int)(mb * 1e6 / per_fit);
+    c = std::max(1, std::min(c, nf));
+    const int n = ceil_div(nf, c);
+    return ceil_div(nf, n);                       // balanced sub-batches
+}
 
 struct Plan {
     std::vector<Group> groups;
@@ -154,41 +175,35 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         g.nf = (int)g.fit_idx.size();
         g.mtiles = ceil_div(g.N, 128);
         g.d_recs = ar.take<FitRec>(g.nf);
+        g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
+        g.chunk = g.use_chain ? chain_chunk_fits(g.N, g.D, g.H, g.L, g.nf) : g.nf;
+        g.nchunks = ceil_div(g.nf, g.chunk);
         const size_t nh = (size_t)g.nf * g.N * g.H, nd = (size_t)g.nf * g.N * g.D;
+        const size_t ch = (size_t)g.chunk * g.N * g.H, cd = (size_t)g.chunk * g.N * g.D;     // one sub-batch
         for (int l = 0; l <= g.L; ++l) {
-            g.act[l] = ar.take<char>(nh * esz);
-            g.cosb[l] = ar.take<char>(nh * esz);
+            g.act[l] = ar.take<char>(ch * esz);
+            g.cosb[l] = ar.take<char>(ch * esz);
         }
-        g.dz[0] = ar.take<char>(nh * esz);
-        g.dz[1] = ar.take<char>(nh * esz);
-        g.dy = ar.take<char>(nd * esz);
+        if (!g.use_chain) { g.dz[0] = ar.take<char>(nh * esz); g.dz[1] = ar.take<char>(nh * esz); }
+        g.dy = ar.take<char>(cd * esz);
         g.yeval = ar.take<float>(nd);
         if (bf) { g.evalact[0] = ar.take<float>(nh); g.evalact[1] = ar.take<float>(nh); }
-        g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
-        // split-K of dW so that the launch fills the GPU: ~2 waves of CTAs on the fp32 path.  On the chain path
-        // it is available for small groups whose dW GEMMs have fewer output tiles than SMs (NERFATTN_DW_SPLIT=1)
-        // but off by default: measured 0.461 vs 0.450 ms per epoch for the dW phase of the 280-fit sweep -- the
-        // small groups' kernels already overlap with the other groups' on the graph's parallel branches
-        int out_tiles = 0, out_tiles_min = 1 << 30;
-        for (int l = 1; l <= g.L + 1; ++l) {
-            out_tiles = std::max(out_tiles, ceil_div(g.lm.out_dim[l], 128) * ceil_div(g.lm.in_dim[l], 128));
-            out_tiles_min = std::min(out_tiles_min, ceil_div(g.lm.out_dim[l], 128) * (g.H / tc::dw_bn(g.H)));
-        }
+        // split-K of dW so that the launch fills the GPU: ~2 waves of CTAs on the fp32 path (partials summed by Adam);
+        // the tensor paths contract all rows of a fit in one tile
         if (bf) {
             g.nsplit = 1;
-            if (g.use_chain && env_flag("NERFATTN_DW_SPLIT"))
-                while (g.nsplit < 4 && g.nsplit * 2 <= g.mtiles && g.nf * out_tiles_min * g.nsplit * 2 <= 148 + 74 &&
-                       (g.N / 64) % (g.nsplit * 2) == 0)
-                    g.nsplit *= 2;
-            g.ksplit = g.N / g.nsplit;
+            g.ksplit = g.N;
         } else {
+            int out_tiles = 0;
+            for (int l = 1; l <= g.L + 1; ++l)
+                out_tiles = std::max(out_tiles, ceil_div(g.lm.out_dim[l], 128) * ceil_div(g.lm.in_dim[l], 128));
             int want = std::max(1, (2 * 148 * 2) / std::max(1, g.nf * out_tiles));
             int max_split = std::max(1, g.N / 256);
             g.nsplit = std::min(want, max_split);
             g.ksplit = (int)align_up((size_t)ceil_div(g.N, g.nsplit), 16);
             g.nsplit = ceil_div(g.N, g.ksplit);
         }
-        g.gradpart = ar.take<float>((size_t)g.nsplit * g.nf * g.lm.P);
+        g.gradpart = g.use_chain ? nullptr : ar.take<float>((size_t)g.nsplit * g.nf * g.lm.P);   // chain: dW goes straight into Adam
         size_t coff = 0;
         for (int l = 0; l <= g.L + 1; ++l) {
             g.colpart_layer_off[l] = coff;
@@ -201,9 +216,18 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         g.losspart = ar.take<float>((size_t)g.nf * g.losspart_per_fit);
         g.wbf16 = bf ? ar.take<__nv_bfloat16>((size_t)g.nf * g.lm.P) : nullptr;
         g.maps = nullptr;
+        g.posid.assign(g.nf, 0);
+        for (int k = 0; k < g.nf; ++k) {
+            const float* pos = fits[g.fit_idx[k]].positions;
+            size_t t = 0;
+            while (t < g.pos_tabs.size() && g.pos_tabs[t] != pos) ++t;
+            if (t == g.pos_tabs.size()) g.pos_tabs.push_back(pos);
+            g.posid[k] = (int)t;
+        }
+        g.d_pos_tabs = g.use_chain ? ar.take<const float*>(g.pos_tabs.size()) : nullptr;
+        g.xop = g.use_chain ? ar.take<__nv_bfloat16>(chain::xop_elems(g.mtiles, (int)g.pos_tabs.size())) : nullptr;
         g.chain_scratch = g.use_chain ? ar.take<__nv_bfloat16>(chain::scratch_elems(g.H, g.L)) : nullptr;
         g.psc = g.use_chain ? ar.take<float>((size_t)g.nf * chain::psc_floats(g.H, g.L)) : nullptr;
-        g.cmaps = nullptr;
     }
     plan.bytes = ar.bytes();
     // stash per-fit unique ids in uniq_first_fit's tail: callers use fit_uniq via closure
@@ -330,6 +354,34 @@ static void fp32_epoch(const Group& g, const Plan& plan, double b1, double b2, d
     launch_adam(g, plan, b1, b2, eps, s);
 }
 
+// one training epoch of one group on the fused chain path (BF16): per sub-batch the row-tile chain, the layer-0
+// gradient and the grouped dW + Adam kernel; then Adam of the 2H layer-0 parameters (it also writes losses[e])
+static int chain_epoch(const Group& g, const Plan& plan, double b1, double b2, double eps, cudaStream_t s) {
+    const int phases = chain::phase_mask();
+    const size_t pscf = chain::psc_floats(g.H, g.L);
+    dw::DwArgs da{};
+    dw::fill_args(da, g.N, g.D, g.H, g.L, g.lm);
+    da.epoch = plan.d_epoch; da.step_size = plan.d_step_size; da.bc2 = plan.d_bc2;
+    da.beta1 = (float)b1; da.beta2 = (float)b2; da.eps = (float)eps;
+    da.wbf16_fit = g.lm.P; da.psc_fit = pscf;
+    int rc;
+    for (int c = 0; c < g.nchunks; ++c) {
+        const int first = c * g.chunk, cnt = std::min(g.chunk, g.nf - first);
+        if ((phases & 1) &&
+            (rc = chain::train_step(g.N, g.D, g.H, g.L, cnt, g.lm, g.d_recs + first, g.cmaps[c], g.chain_scratch,
+                                    g.losspart + (size_t)first * g.losspart_per_fit, g.losspart_per_fit, g.mtiles,
+                                    g.psc + (size_t)first * pscf, g.xpart + (size_t)first * g.mtiles * g.H,
+                                    g.colpart + g.colpart_layer_off[0] + (size_t)first * g.mtiles * g.H, s))) return rc;
+        if (!(phases & 2)) continue;
+        da.nf = cnt; da.recs = g.d_recs + first;
+        da.wbf16 = g.wbf16 + (size_t)first * g.lm.P;
+        da.psc = g.psc + (size_t)first * pscf;
+        if ((rc = dw::launch(g.dmaps, da, s))) return rc;
+    }
+    if (phases & 4) launch_adam(g, plan, b1, b2, eps, s, /*layer0_only=*/true);
+    return NA_OK;
+}
+
 // final evaluation: fp32 forward with the trained weights + metrics (siren.py:119-125).
 // Always fp32 SIMT, also in the BF16 mode: the numbers must be what torch's model(positions)
 // gives for the returned weights.
@@ -370,6 +422,62 @@ static void reap_graphs() {
     cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error of ours
 }
 
+
+// Streams and events of a graph capture (one capture stream, one side stream + join event per shape group, one
+// fork event).  Creating and destroying them per call costs more than the capture itself, so they are pooled per
+// device; a Lease hands one kit to a call and returns it when the call leaves, on every path.
+struct CaptureKit {
+    int device = -1;
+    cudaStream_t cap = nullptr;
+    cudaEvent_t fork = nullptr;
+    std::vector<cudaStream_t> side;
+    std::vector<cudaEvent_t> joins;
+    bool grow(size_t nside) {
+        if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (!fork && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        while (side.size() < nside) {
+            cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return false;
+            side.push_back(st);
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+            joins.push_back(ev);
+        }
+        return true;
+    }
+};
+static std::mutex g_kit_mu;
+static std::vector<CaptureKit*> g_kits;          // idle kits of every device
+struct KitLease {
+    CaptureKit* kit = nullptr;
+    explicit KitLease(size_t nside) {
+        const int dev = tc::current_device();
+        {
+            std::lock_guard<std::mutex> lk(g_kit_mu);
+            for (size_t i = 0; i < g_kits.size(); ++i)
+                if (g_kits[i]->device == dev) { kit = g_kits[i]; g_kits[i] = g_kits.back(); g_kits.pop_back(); break; }
+        }
+        if (!kit) { kit = new CaptureKit(); kit->device = dev; }
+        if (!kit->grow(nside)) {                  // leave what exists in the pool; the caller reports the CUDA error
+            std::lock_guard<std::mutex> lk(g_kit_mu);
+            g_kits.push_back(kit);
+            kit = nullptr;
+        }
+    }
+    ~KitLease() {
+        if (!kit) return;
+        std::lock_guard<std::mutex> lk(g_kit_mu);
+        g_kits.push_back(kit);
+    }
+    KitLease(const KitLease&) = delete;
+    KitLease& operator=(const KitLease&) = delete;
+};
+// A captured graph and its executable: destroyed on scope exit unless handed to park_graph()
+struct GraphHold {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    ~GraphHold() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); }
+    void release() { graph = nullptr; exec = nullptr; }
+};
+
 }  // namespace na
 
 // =========================================================================== C ABI
@@ -400,7 +508,7 @@ extern "C" long long nerfattn_fit_launch_count(const na_fit_t* fits, int32_t nfi
     long long per_epoch = 1 /* tick */, fin = 0;
     for (const Group& g : plan.groups) {
         // layer0 + L fwd + out + (L+1) x (dW, dX) + Adam; the tensor path adds the layer-0 gradient kernel
-        if (g.use_chain) per_epoch += 1 + (g.L + 1) + 1 + 1;      // chain + dW per layer + layer-0 gradient + Adam
+        if (g.use_chain) per_epoch += 2 * g.nchunks + 1;          // per sub-batch: chain, dW + Adam; then Adam of layer 0
         else per_epoch += 1 + g.L + 1 + 2 * (g.L + 1) + 1 + (precision == NA_PREC_BF16 ? 1 : 0);
         fin += 1 + g.L + 1 + 2;
         if (precision == NA_PREC_BF16) setup += 1;   // bf16 weight mirror
@@ -467,6 +575,8 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             r.params = f.params; r.m = f.adam_m; r.v = f.adam_v; r.losses = f.losses;
             r.cos = f.cos_sims; r.ppmse = f.per_pos_mse; r.scalars = f.scalars;
             r.mean_out = f.mean; r.std_out = f.std; r.omega = f.omega0; r.uniq = u; r.fit_index = g.fit_idx[k];
+            r.prenorm = (f.flags & NA_FIT_TARGETS_PRENORMALISED) ? 1 : 0;
+            r.posid = g.posid[k];
         }
         NA_CUDA_OK(cudaMemcpyAsync(g.d_recs, recs.data(), g.nf * sizeof(FitRec), cudaMemcpyHostToDevice, stream));
     }
@@ -518,18 +628,29 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
 
     // ---- tensor path set-up: TMA descriptors + initial bf16 weight mirror
     std::vector<tc::GroupMaps> maps(plan.groups.size());
-    std::vector<chain::ChainMaps> cmaps(plan.groups.size());
     if (precision == NA_PREC_BF16) {
         if ((rc = tc::configure_all())) return rc;
         if ((rc = chain::configure_all())) return rc;
+        if ((rc = dw::configure_all())) return rc;
         for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
             Group& g = plan.groups[gi];
-            g.maps = &maps[gi];
-            g.cmaps = &cmaps[gi];
-            rc = tc::build_group_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.act, g.cosb, g.dz, g.dy, g.wbf16, *g.maps,
-                                      g.use_chain ? g.cosb : nullptr);
-            if (rc) return rc;
-            if (g.use_chain && (rc = chain::build_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.wbf16, g.act, g.cosb, g.dy, *g.cmaps))) return rc;
+            if (g.use_chain) {
+                g.cmaps.resize(g.nchunks);
+                for (int c = 0; c < g.nchunks; ++c) {
+                    const int first = c * g.chunk, cnt = std::min(g.chunk, g.nf - first);
+                    if ((rc = chain::build_maps(g.N, g.D, g.H, g.L, cnt, g.lm, g.wbf16 + (size_t)first * g.lm.P, g.act, g.cosb,
+                                                g.dy, g.xop, g.mtiles * (int)g.pos_tabs.size(), g.cmaps[c]))) return rc;
+                }
+                NA_CUDA_OK(cudaMemcpyAsync(g.d_pos_tabs, g.pos_tabs.data(), g.pos_tabs.size() * sizeof(float*),
+                                           cudaMemcpyHostToDevice, stream));
+                chain::xop_kernel<<<dim3(g.mtiles, (unsigned)g.pos_tabs.size()), tc::BM, 0, stream>>>(g.d_pos_tabs, g.N, g.mtiles, g.xop);
+                NA_LAUNCH_OK("xop_kernel");
+                if ((rc = dw::build_maps(g.N, g.D, g.H, g.L, g.chunk, g.act, g.cosb, g.dy, g.dmaps))) return rc;
+            } else {
+                g.maps = &maps[gi];
+                if ((rc = tc::build_group_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.act, g.cosb, g.dz, g.dy, g.wbf16, *g.maps)))
+                    return rc;
+            }
             tc::mirror_weights(g.d_recs, g.lm, g.nf, g.wbf16, stream);
             if (g.psc) chain::scale_params(g.d_recs, g.nf, g.H, g.L, g.psc, stream);
             NA_LAUNCH_OK("mirror_weights");
@@ -546,22 +667,15 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             if (parallel) cudaStreamWaitEvent(s, fork, 0);
             const Group& g = plan.groups[gi];
             if (precision == NA_PREC_FP32) fp32_epoch(g, plan, beta1, beta2, eps, s);
-            else {
-                chain::AdamFuse af{};
-                const bool fused = g.use_chain && chain::adam_fused();
-                if (fused) {
-                    af.epoch = plan.d_epoch; af.step_size = plan.d_step_size; af.bc2 = plan.d_bc2;
-                    af.beta1 = (float)beta1; af.beta2 = (float)beta2; af.eps = (float)eps; af.wbf16 = g.wbf16;
-                }
-                int r2 = g.use_chain
-                    ? chain::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, *g.cmaps, g.act, g.cosb, g.dy,
-                                   g.chain_scratch, g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                   g.losspart_per_fit, g.mtiles, af, g.nsplit, g.psc, s)
-                    : tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
-                                g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                g.losspart_per_fit, g.mtiles, s);
+            else if (g.use_chain) {
+                int r2 = chain_epoch(g, plan, beta1, beta2, eps, s);
                 if (r2) return r2;
-                if (!g.use_chain || (chain::phase_mask() & 4)) launch_adam(g, plan, beta1, beta2, eps, s, fused);
+            } else {
+                int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
+                                   g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
+                                   g.losspart_per_fit, g.mtiles, s);
+                if (r2) return r2;
+                launch_adam(g, plan, beta1, beta2, eps, s);
             }
             if (parallel) { cudaEventRecord(joins[gi], s); cudaStreamWaitEvent(main, joins[gi], 0); }
         }
@@ -586,35 +700,26 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     if (epochs > 0) {
         const bool use_graph = !env_flag("NERFATTN_NO_GRAPH");
         if (use_graph) {
-            cudaStream_t cap;
-            NA_CUDA_OK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-            std::vector<cudaStream_t> side(plan.groups.size() > 1 ? plan.groups.size() : 0);
-            std::vector<cudaEvent_t> joins(side.size());
-            cudaEvent_t fork = nullptr;
-            for (auto& s : side) NA_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-            for (auto& e : joins) NA_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            NA_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
-            NA_CUDA_OK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-            rc = record_epoch(cap, side, fork, joins);
-            cudaError_t ce = cudaStreamEndCapture(cap, &graph);
-            if (rc == NA_OK && ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
-            if (rc == NA_OK) {
-                ce = cudaGraphInstantiate(&exec, graph, 0);
-                if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
-            }
-            for (int e = 0; rc == NA_OK && e < epochs; ++e) {
-                if ((rc = log_progress(e))) break;
-                ce = cudaGraphLaunch(exec, stream);
-                if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); rc = NA_ERR_CUDA; }
-            }
-            if (exec && rc == NA_OK) park_graph(exec, graph, stream);
-            else { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); }
-            for (auto& s : side) cudaStreamDestroy(s);
-            for (auto& e : joins) cudaEventDestroy(e);
-            cudaEventDestroy(fork);
-            cudaStreamDestroy(cap);
+            const size_t nside = plan.groups.size() > 1 ? plan.groups.size() : 0;
+            KitLease lease(nside);
+            if (!lease.kit) { set_error("cannot create capture streams / events: %s", cudaGetErrorString(cudaGetLastError())); return NA_ERR_CUDA; }
+            std::vector<cudaStream_t> side(lease.kit->side.begin(), lease.kit->side.begin() + nside);
+            std::vector<cudaEvent_t> joins(lease.kit->joins.begin(), lease.kit->joins.begin() + nside);
+            GraphHold gh;
+            NA_CUDA_OK(cudaStreamBeginCapture(lease.kit->cap, cudaStreamCaptureModeThreadLocal));
+            rc = record_epoch(lease.kit->cap, side, lease.kit->fork, joins);
+            cudaError_t ce = cudaStreamEndCapture(lease.kit->cap, &gh.graph);      // always ends the capture, also after an error
             if (rc) return rc;
+            if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
+            ce = cudaGraphInstantiate(&gh.exec, gh.graph, 0);
+            if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
+            for (int e = 0; e < epochs; ++e) {
+                if ((rc = log_progress(e))) return rc;
+                ce = cudaGraphLaunch(gh.exec, stream);
+                if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
+            }
+            park_graph(gh.exec, gh.graph, stream);          // still running: destroyed by a later call
+            gh.release();
         } else {
             std::vector<cudaStream_t> none; std::vector<cudaEvent_t> nonej;
             for (int e = 0; e < epochs; ++e) {

@@ -31,6 +31,13 @@
 
 #include "siren_tc.cuh"
 
+// profiling-only debug addressing (libnerfattn_prof.so, -DNA_PROFILING); constant 0 in the release library
+#ifdef NA_PROFILING
+#define NA_DBG(g) ((g).dbg)
+#else
+#define NA_DBG(g) 0
+#endif
+
 namespace na {
 namespace chain {
 
@@ -71,14 +78,17 @@ struct ChainArgs {
     const float* dotvec; float* dotpart;    // forward-only (decode): u [nf][H] fp32, partial scores [nf][CG][N]
     const float* pvec; float* pvpart;       // forward-only (decode, values): p [nf][N] fp32, partial sums [nf][N/32][H]
     const float* psc; int psc_fit;          // per fit w*W0[H], w*b0[H], w*b_1[H] .. w*b_L[H] (scale_params_kernel; Adam keeps it current)
-    int dbg;                                // NERFATTN_CHAIN_DBG (profiling experiments only)
+    float* xpart; float* colpart0;          // training: layer-0 gradient partials per row tile [nf][mtiles][H]: sum_r dz0[r][j] x[r], sum_r dz0[r][j]
+    int dbg;                                // NERFATTN_CHAIN_DBG (libnerfattn_prof.so only; 0 in the release library)
     int sincos_mode;                        // bit 0: hidden layers, bit 1: layer 0 use the MUFU-core sincos (common.cuh)
 };
 // wk / wmn: weights of layers 1..L+1 as K-major (forward) and MN-major (backward) B operands (loads);
 // hout[l] / zout[l] / yout: h_l, dz_l [nf][N][H] and dY [nf][N][D] as 64 x 128 boxes (stores)
+// xop: the B operand of the layer-0 gradient MMA, [position table][row tile][16][128] bf16 (xop_kernel)
 struct ChainMaps {
     CUtensorMap wk[kMaxHidden + 2]; CUtensorMap wmn[kMaxHidden + 2];
     CUtensorMap hout[kMaxHidden + 1]; CUtensorMap zout[kMaxHidden + 1]; CUtensorMap yout;
+    CUtensorMap xop;
 };
 
 // Any sequence length: the last row tile may be ragged (rows >= N are masked out of the loss, produce dY = 0 and
@@ -159,9 +169,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* local_bar, uint32_
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_bar)), "r"(cta_rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
-__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool b_mn, bool a_mn = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
 }
+constexpr int XOP_N = 16;                         // rows of the layer-0 gradient operand: ones, x_hi, x_mid, x_lo, 12 x zero
+constexpr int XOP_BYTES = XOP_N * BM * 2;         // one row tile of it: [16][128] bf16 = two 64-K chunks of 2 KB
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -314,7 +327,27 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             }
             for (int round = 0;; ++round) {
                 if (tile_of(round, 0) >= total_tiles) break;
-                for (int s = 1; s < nsteps; ++s) {
+                for (int s = 1; s <= (FWD ? nsteps - 1 : nsteps); ++s) {
+                    if (s == nsteps) {
+                        // training: the B operand of the layer-0 gradient MMA (positions of this row tile, siren_chain.cuh
+                        // "layer-0 gradient"): one 4 KB stage per tile, two 64-K chunks of [16][64] bf16
+                        for (int slot = 0; slot < NSLOT; ++slot) {
+                            const int tile = tile_of(round, slot);
+                            if (tile >= total_tiles) break;
+                            const int fit = tile / g.mtiles, mt = tile - fit * g.mtiles;
+                            const int xrow = g.recs[fit].posid * g.mtiles + mt;
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            if (CL == 1 || crank == 0) mbar_expect_tx(&full[stage], (uint32_t)(CL * XOP_BYTES));
+                            uint8_t* sb = smem_ring + stage * STAGE_SZ;
+                            const uint32_t lbar = (CL == 2) ? mapa_u32(&full[stage], 0) : 0u;
+                            for (int c = 0; c < 2; ++c) {
+                                if (CL == 1 || crank == 0) tma_load_3d(sb + c * (XOP_BYTES / 2), &maps.xop, &full[stage], c * 64, 0, xrow);
+                                else tma_load_3d_2cta(sb + c * (XOP_BYTES / 2), &maps.xop, lbar, c * 64, 0, xrow);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        continue;
+                    }
                     const Step st = step_info<H>(s, L, D);
                     const CUtensorMap* map = st.mn ? &maps.wmn[st.layer] : &maps.wk[st.layer];
                     const uint32_t tx = (uint32_t)st.n * 128u;           // both halves land on the leader's barrier when CL == 2
@@ -377,13 +410,37 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     tc_fence_after();
                     uint8_t* const act = smem + slot * C::ACT_BYTES;
                     if (s == nsteps) {
-                        // No MMA: acknowledge the phase.  The next tile's E0 waits for this, otherwise a fast slot could
-                        // complete act_ready twice before this warp looked at it (parity waits alias after two phases).
+                        // Layer-0 gradient of this tile: the buffer holds dz_0 [128 rows x H] bf16.  Read as an MN-major A
+                        // operand (M = 128 columns of dz_0 per MMA, K = the 128 rows) and contracted with the [16 x 128]
+                        // operand {1, x_hi, x_mid, x_lo} of the tile's positions it gives sum_r dz0[r][j] and
+                        // sum_r dz0[r][j] x[r] (x exact: three bf16 pieces) in 16 accumulator columns per 128 columns of
+                        // dz_0 -- dz_0 never goes to HBM and there is no separate gradient kernel.  The commit on
+                        // acc_full also acknowledges the phase: the next tile's E0 waits for it (a fast slot must not
+                        // complete act_ready twice before this warp looked at it: parity waits alias after two phases),
+                        // drains these columns, and only then rewrites the buffer.
+                        constexpr int NH = (H >= 128) ? H / 128 : 1;
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
                         if (lane == 0) {
-                            mbar_arrive(&acc_full[slot]);
-                            if (CL == 2) mbar_arrive_cluster(&acc_full[slot], 1);
+                            const uint32_t act_u32 = smem_u32(act);
+                            const uint32_t xb = smem_u32(smem_ring + stage * STAGE_SZ);
+                            const uint32_t xidesc = (CL == 2) ? make_idesc_m(256, 2 * XOP_N, false, true) : make_idesc(XOP_N, true, false);
+#pragma unroll
+                            for (int mh = 0; mh < NH; ++mh) {
+                                const uint32_t d_tmem = tmem_base + slot * C::ACC_COLS + mh * (CL * XOP_N);
+#pragma unroll
+                                for (int k = 0; k < BM / UMMA_K; ++k) {
+                                    const uint64_t adesc = make_desc(act_u32 + mh * 2 * CHUNK_BYTES + k * (UMMA_K * 128), CHUNK_BYTES, 1024);
+                                    const uint64_t bdesc = make_desc(xb + (k >> 2) * (XOP_BYTES / 2) + (k & 3) * (UMMA_K * 2), 0, 1024);
+                                    if (CL == 2) tc_mma_bf16_2cta(d_tmem, adesc, bdesc, xidesc, k > 0 ? 1u : 0u);
+                                    else tc_mma_bf16(d_tmem, adesc, bdesc, xidesc, k > 0 ? 1u : 0u);
+                                }
+                            }
+                            if (CL == 2) { tc_commit_2cta(&empty[stage], 3); tc_commit_2cta(&acc_full[slot], 3); }
+                            else { tc_commit(&empty[stage]); tc_commit(&acc_full[slot]); }
                         }
                         __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     const uint32_t act_u32 = smem_u32(act);
@@ -438,10 +495,10 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     mbar_wait(&act_ready[slot], (rdy_phase >> slot) & 1u);
                     rdy_phase ^= 1u << slot;
                     if (lane == 0) {
-                        if (!(g.dbg & 1)) {
+                        if (ps < nsteps - 1 && !(NA_DBG(g) & 1)) {       // dz_0 (the last step) is consumed on the SM: no store
                             const uint8_t* act = smem + slot * C::ACT_BYTES;
                             for (int kc = 0; kc < ochunks; ++kc)
-                                tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, ((g.dbg & 4) ? (int)(blockIdx.x % g.mtiles) : mt) * BM, (g.dbg & 4) ? 0 : fit, pol_stream);
+                                tma_store_3d(omap, act + kc * CHUNK_BYTES, kc * 64, ((NA_DBG(g) & 4) ? (int)(blockIdx.x % g.mtiles) : mt) * BM, (NA_DBG(g) & 4) ? 0 : fit, pol_stream);
                             tma_store_commit();
                             tma_store_wait_read();
                         }
@@ -476,6 +533,23 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         // rows, 32 B each) touch 1 KB of contiguous memory per access instead of 32 lines at row stride
         constexpr int SCR_U = BM * 16;                // elements between consecutive 16-column units
         uint32_t acc_phase = 0, free_phase = 0;       // bit `slot` = parity of acc_full[slot] / buf_free[slot]
+        // Layer-0 gradient partials of the tile a slot has just finished: the MMA warp left sum_r dz0[r][j] {1, x_hi, x_mid,
+        // x_lo}[r] in 16 accumulator columns per 128 columns of dz_0 (lane = column j); the column group cg drains the
+        // cg-th block.  Per-tile partials, summed over the row tiles in a fixed order by adam_kernel: deterministic.
+        constexpr int L0_NH = (H >= 128) ? H / 128 : 1;
+        auto drain_l0grad = [&](int slot, int pfit, int pmt) {
+            if (cg < L0_NH) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + cg * (CL * XOP_N) + (int)crank * XOP_N, v);
+                tmem_ld_wait();
+                const int j = cg * 128 + q * 32 + lane;
+                if (j < H) {
+                    const size_t o = ((size_t)pfit * g.mtiles + pmt) * H + j;
+                    g.colpart0[o] = __uint_as_float(v[0]);
+                    g.xpart[o] = (__uint_as_float(v[1]) + __uint_as_float(v[2])) + __uint_as_float(v[3]);
+                }
+            }
+        };
 #ifdef NA_CHAIN_TIMING
         long long t_acc = 0, t_kind[4] = {0, 0, 0, 0}, t_begin = clock64(), tq = 0, ts = 0, t_acc0 = 0;
 #define NA_T0() tq = clock64()
@@ -484,7 +558,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #define NA_T0()
 #define NA_T1()
 #endif
-        for (int round = 0;; ++round) {
+        int round = 0;
+        for (;; ++round) {
             // the tiles of this round (per slot), resolved once: the step bodies below run 2 x nsteps times per round
             const int tile0 = tile_of(round, 0), tile1 = (NSLOT > 1) ? tile_of(round, 1) : total_tiles;
             if (tile0 >= total_tiles) break;
@@ -513,9 +588,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     // the buffer is free once the MMA warp has stored the previous tile's dz_0
                     if (!FWD && round > 0) {
                         NA_T0();
-                        mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;       // the MMA warp has seen the last step
-                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;     // the store warp has stored dz_0
+                        mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;       // the layer-0 gradient MMA of the previous tile is complete
+                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;     // the store warp has seen the last step
                         NA_T1();
+                        tc_fence_after();
+                        const int ptile = tile_of(round - 1, slot), pfit = ptile / g.mtiles;
+                        drain_l0grad(slot, pfit, ptile - pfit * g.mtiles);
                     }
                     // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
                     const float x = __ldg(rec->pos + row_c);
@@ -761,6 +839,18 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             }
             }
         }
+        if (!FWD) {
+            // the last tile of each slot: its layer-0 gradient MMA is the last thing the tensor core does for this CTA
+#pragma unroll 1
+            for (int slot = 0; slot < NSLOT; ++slot) {
+                const int ptile = (round > 0) ? tile_of(round - 1, slot) : total_tiles;
+                if (ptile >= total_tiles) continue;
+                const int pfit = ptile / g.mtiles;
+                mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                tc_fence_after();
+                drain_l0grad(slot, pfit, ptile - pfit * g.mtiles);
+            }
+        }
 #ifdef NA_CHAIN_TIMING
         if (lane == 0 && (ei == 0 || ei == 5) && (blockIdx.x == 0 || blockIdx.x == 77))
             printf("chain timing cta %d warp %d: total %lld wait_acc %lld E0 %lld sine %lld out %lld dx %lld\n", (int)blockIdx.x,
@@ -799,9 +889,29 @@ inline size_t scratch_elems(int H, int L) {
     return (size_t)num_sms() * 2 * (L + 1) * BM * H;
 }
 
+// B operand of the layer-0 gradient MMA for every row tile of one position vector: xop[tile][j][r], r = row inside the
+// tile, j = 0: 1, j = 1..3: the three bf16 pieces of x[r] (x_hi + x_mid + x_lo == x to fp32 precision, so the product
+// with the bf16 dz_0 is exact), j >= 4: 0.  Rows past the sequence are all-zero.  grid (mtiles, tables), block 128.
+__global__ void xop_kernel(const float* const* pos_tab, int N, int mtiles, __nv_bfloat16* xop) {
+    const int row = blockIdx.x * BM + threadIdx.x;
+    const bool ok = row < N;
+    const float x = ok ? pos_tab[blockIdx.y][row] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    __nv_bfloat16* dst = xop + ((size_t)blockIdx.y * mtiles + blockIdx.x) * (XOP_N * BM) + threadIdx.x;
+    dst[0] = __float2bfloat16_rn(ok ? 1.f : 0.f);
+    dst[BM] = hi; dst[2 * BM] = mid; dst[3 * BM] = lo;
+    for (int j = 4; j < XOP_N; ++j) dst[j * BM] = __float2bfloat16_rn(0.f);
+}
+inline size_t xop_elems(int mtiles, int ntab) { return (size_t)ntab * mtiles * XOP_N * BM; }
+
 inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __nv_bfloat16* wbf16,
-                      void* const* act, void* const* dzs, void* dy, ChainMaps& m) {
+                      void* const* act, void* const* dzs, void* dy, const __nv_bfloat16* xop, int xop_tiles, ChainMaps& m) {
     int rc;
+    // [tile][16][128]: box {64 K, 16 rows}, two boxes per tile
+    if ((rc = make_map(&m.xop, xop, BM, XOP_N, xop_tiles, BM, (uint64_t)XOP_N * BM, 64, XOP_N))) return rc;
     for (int l = 0; l <= L; ++l) {
         if ((rc = make_operand_map(&m.hout[l], act[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
         if ((rc = make_operand_map(&m.zout[l], dzs[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
@@ -865,14 +975,22 @@ inline int sincos_mode() {
     const char* e = getenv("NERFATTN_SINCOS");
     return e ? (int)strtol(e, nullptr, 0) & 3 : 3;
 }
-// NERFATTN_PHASE (profiling only; results are meaningless): 1 = launch only the chain kernels of an
-// epoch, 2 = only the dW GEMMs + layer-0 gradient, 4 = only Adam; 0 / unset = everything.  bench.py
-// uses it to time the dominant kernel alone, live, with CUDA events.
+// Profiling switches exist only in libnerfattn_prof.so (-DNA_PROFILING, `make libnerfattn_prof.so`); the release
+// library always launches every kernel and has no debug addressing.
+// NERFATTN_PHASE (results are meaningless): 1 = launch only the chain kernels of an epoch, 2 = only the dW GEMMs
+// (+ their fused Adam), 4 = only the stand-alone Adam kernels; 8 = none; 0 / unset = everything.  bench.py loads the
+// profiling build beside the release one to time the dominant kernel alone, live, with CUDA events.
+#ifdef NA_PROFILING
 inline int phase_mask() {
     const char* e = getenv("NERFATTN_PHASE");
     const int m = e ? atoi(e) : 0;
     return m ? m : 7;
 }
+inline int chain_dbg() { const char* e = getenv("NERFATTN_CHAIN_DBG"); return e ? atoi(e) : 0; }
+#else
+constexpr int phase_mask() { return 7; }
+constexpr int chain_dbg() { return 0; }
+#endif
 
 // One training epoch of one group: the chain, then the dW GEMMs (contraction over all rows of a fit)
 // and the layer-0 gradient; Adam follows in the caller.
@@ -892,53 +1010,22 @@ inline void scale_params(const FitRec* recs, int n, int H, int L, float* psc, cu
     scale_params_kernel<<<n, 256, 0, s>>>(recs, H, L, nullptr, psc);
 }
 
-struct AdamFuse {            // non-null epoch => the dW epilogues apply Adam to layers 1..L+1 (siren_tc.cuh)
-    const int* epoch; const float* step_size; const float* bc2; float beta1, beta2, eps;
-    __nv_bfloat16* wbf16;
-};
-// measured on B200: 2.01 ms per epoch fused vs 1.92 ms with the separate coalesced adam_kernel (the dW epilogue owns one
-// row per thread, so its p/m/v accesses are 32 B per lane at row stride) -- off by default
-inline bool adam_fused() { const char* e = getenv("NERFATTN_ADAM_FUSED"); return e ? atoi(e) != 0 : false; }
-
-inline int epoch(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const GroupMaps& m,
-                 const ChainMaps& cm, void* const* act, void* const* dzs, void* dy, __nv_bfloat16* scratch,
-                 float* gradpart, float* colpart, const size_t* colpart_layer_off, float* xpart, float* losspart,
-                 int losspart_per_fit, int mtiles, const AdamFuse& af, int ksplits, const float* psc, cudaStream_t s) {
-    int rc;
+// One training step of one group (or sub-batch of a group): forward, loss and the dX chain of every 128-row tile.
+// The weight gradients and Adam follow in dw::dw_adam_kernel (siren_dw.cuh), the layer-0 parameters in adam_kernel.
+inline int train_step(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
+                      __nv_bfloat16* scratch, float* losspart, int losspart_per_fit, int mtiles, const float* psc,
+                      float* xpart, float* colpart0, cudaStream_t s) {
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
-    (void)act; (void)dy;                       // written through the TMA store maps in `cm`
     a.scratch = scratch;
     a.losspart = losspart; a.losspart_per_fit = losspart_per_fit;
     a.loss_scale = 2.0f / ((float)N * (float)D);
     a.sincos_mode = sincos_mode();
     a.psc = psc; a.psc_fit = (int)psc_floats(H, L);
-    { const char* e = getenv("NERFATTN_CHAIN_DBG"); a.dbg = e ? atoi(e) : 0; }
-    const int phases = phase_mask();
-    if ((phases & 1) && (rc = launch(H, cm, a, 0, s))) return rc;
-    if (!(phases & 2)) return NA_OK;
-    TcArgs base{};
-    base.nb = nf; base.recs = recs;
-    for (int l = L + 1; l >= 1; --l) {
-        const int width = lm.out_dim[l];
-        TcArgs w = base;
-        w.M = width; w.N = H; w.K = N;
-        w.fout = gradpart; w.fout_fit = lm.P; w.fout_off = lm.w_off[l]; w.ldf = H;
-        w.biasgrad = colpart + colpart_layer_off[l]; w.biasgrad_fit = (size_t)ksplits * width;
-        w.ksplits = ksplits; w.fout_split = (size_t)nf * lm.P;
-        if (af.epoch && (phases & 4) && ksplits == 1) {
-            w.adam_epoch = af.epoch; w.adam_step_size = af.step_size; w.adam_bc2 = af.bc2;
-            w.adam_beta1 = af.beta1; w.adam_beta2 = af.beta2; w.adam_eps = af.eps;
-            w.adam_w_off = lm.w_off[l]; w.adam_b_off = lm.b_off[l];
-            w.adam_wbf16 = af.wbf16; w.adam_wbf16_fit = lm.P;
-            if (l <= L) { w.adam_psc = const_cast<float*>(psc); w.adam_psc_fit = psc_floats(H, L); w.adam_psc_off = (l + 1) * H; }
-        }
-        if ((rc = launch_bn<kDw, true, true>(dw_bn(H), m.dw[l], w, s))) return rc;
-    }
-    layer0_grad_kernel<<<dim3(mtiles, nf), 256, 0, s>>>(recs, (const __nv_bfloat16*)dzs[0], (size_t)N * H, N, H, mtiles,
-                                                        xpart, colpart + colpart_layer_off[0]);
-    return NA_OK;
+    a.xpart = xpart; a.colpart0 = colpart0;
+    a.dbg = chain_dbg();
+    return launch(H, cm, a, 0, s);
 }
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).

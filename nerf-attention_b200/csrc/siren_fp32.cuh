@@ -405,6 +405,17 @@ struct AdamArgs {
     int p_end;              // parameters [0, p_end) are updated here (the rest in the dW epilogues when fused)
 };
 
+// One parameter of torch _single_tensor_adam (non-capturable branch), in torch's operation order and with IEEE
+// roundings: lerp_, mul_ + addcmul_, sqrt / bias_correction2_sqrt + eps, addcdiv_(value = -step_size).
+// ob1 = 1 - beta1, ob2 = 1 - beta2, nss = -step_size.  Shared by adam_kernel and the fused dW epilogue (siren_dw.cuh).
+__device__ __forceinline__ void adam_update(float g, float& m, float& v, float& w, float ob1, float beta2, float ob2,
+                                            float eps, float bc2, float nss) {
+    m = __fadd_rn(m, __fmul_rn(ob1, __fsub_rn(g, m)));
+    v = __fadd_rn(__fmul_rn(v, beta2), __fmul_rn(__fmul_rn(ob2, g), g));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2), eps);
+    w = __fadd_rn(w, __fdiv_rn(__fmul_rn(nss, m), denom));
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     const int f = blockIdx.y;
     const FitRec& rec = a.recs[f];
@@ -450,12 +461,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
     const float bc2 = a.et.bc2_sqrt[e], nss = -a.et.step_size[e];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        m[i] = __fadd_rn(m[i], __fmul_rn(1.0f - a.beta1, __fsub_rn(gs[i], m[i])));
-        v[i] = __fadd_rn(__fmul_rn(v[i], a.beta2), __fmul_rn(__fmul_rn(1.0f - a.beta2, gs[i]), gs[i]));
-        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v[i]), bc2), a.eps);
-        w[i] = __fadd_rn(w[i], __fdiv_rn(__fmul_rn(nss, m[i]), denom));
-    }
+    for (int i = 0; i < 4; ++i) adam_update(gs[i], m[i], v[i], w[i], 1.0f - a.beta1, a.beta2, 1.0f - a.beta2, a.eps, bc2, nss);
     *reinterpret_cast<float4*>(rec.m + p) = make_float4(m[0], m[1], m[2], m[3]);
     *reinterpret_cast<float4*>(rec.v + p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(rec.params + p) = make_float4(w[0], w[1], w[2], w[3]);
@@ -494,7 +500,7 @@ row_metrics_kernel(const FitRec* recs, const float* y, size_t y_fit, int N, int 
     float pp = 0.f, tt = 0.f, se = 0.f;
     for (int d = lane; d < D; d += 32) {
         const float pr = fmaf(yr[d], rec.stdv[d], rec.mean[d]);   // pred_norm * std + mean
-        const float t = tr[d];
+        const float t = rec.prenorm ? fmaf(tr[d], rec.stdv[d], rec.mean[d]) : tr[d];   // pre-normalised targets: back to real units
         pp = fmaf(pr, pr, pp); tt = fmaf(t, t, tt);
         const float e = pr - t; se = fmaf(e, e, se);
     }
@@ -509,7 +515,8 @@ row_metrics_kernel(const FitRec* recs, const float* y, size_t y_fit, int N, int 
     float dot = 0.f;
     for (int d = lane; d < D; d += 32) {
         const float pr = fmaf(yr[d], rec.stdv[d], rec.mean[d]);
-        dot = fmaf(pr / np, tr[d] / nt, dot);
+        const float t = rec.prenorm ? fmaf(tr[d], rec.stdv[d], rec.mean[d]) : tr[d];
+        dot = fmaf(pr / np, t / nt, dot);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);

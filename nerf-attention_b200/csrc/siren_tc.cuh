@@ -62,13 +62,6 @@ struct TcArgs {
     int ksplits; size_t fout_split;                       // kDw: split-K (partials [ksplits][...], summed by Adam)
     float* losspart; int losspart_per_fit;                // kFwdOut
     float loss_scale;
-    // kDw with Adam fused into the epilogue (chain mode): the gradient tile goes straight from TMEM into
-    // torch's _single_tensor_adam update of W_l / b_l, never through HBM (adam_kernel then only does layer 0)
-    const int* adam_epoch; const float* adam_step_size; const float* adam_bc2;   // device epoch counter + tables
-    float adam_beta1, adam_beta2, adam_eps;
-    int adam_w_off, adam_b_off;                           // offsets of W_l / b_l in the packed parameter vector
-    __nv_bfloat16* adam_wbf16; size_t adam_wbf16_fit;     // bf16 mirror the MMAs read
-    float* adam_psc; size_t adam_psc_fit; int adam_psc_off;   // omega-prescaled bias copy the chain kernel reads (or null)
     const float* dotvec; size_t dotvec_fit;               // kFwdDot: u [N] per fit (fp32)
     float* dotpart; size_t dotpart_fit;                   // kFwdDot: [n_tiles*2][M] partial row sums
 };
@@ -354,44 +347,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
 
-            float adam_bc2v = 1.f, adam_nss = 0.f;
-            if (MODE == kDw && g.adam_epoch != nullptr) {
-                const int e = *g.adam_epoch;
-                adam_bc2v = g.adam_bc2[e]; adam_nss = -g.adam_step_size[e];
-            }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
 
             auto process = [&](const uint32_t (&v)[32], int c) {
                 const int col = col_base + c * 32;
-                if (MODE == kDw && g.adam_epoch != nullptr) {
-                    if (row_ok) {
-                        const FitRec* rec = &g.recs[b];
-                        const size_t p0 = (size_t)g.adam_w_off + (size_t)row * g.ldf + col;
-                        float* pw = rec->params + p0; float* pm = rec->m + p0; float* pv = rec->v + p0;
-                        __nv_bfloat16* pb = g.adam_wbf16 + (size_t)b * g.adam_wbf16_fit + p0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint32_t w8[8], m8[8], v8[8], o8[4];
-                            ld_global_256(pw + j, w8); ld_global_256(pm + j, m8); ld_global_256(pv + j, v8);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const float gr = __uint_as_float(v[j + k]);
-                                float mm = __uint_as_float(m8[k]), vv = __uint_as_float(v8[k]), ww = __uint_as_float(w8[k]);
-                                mm = __fadd_rn(mm, __fmul_rn(1.0f - g.adam_beta1, __fsub_rn(gr, mm)));
-                                vv = __fadd_rn(__fmul_rn(vv, g.adam_beta2), __fmul_rn(__fmul_rn(1.0f - g.adam_beta2, gr), gr));
-                                const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), adam_bc2v), g.adam_eps);
-                                ww = __fadd_rn(ww, __fdiv_rn(__fmul_rn(adam_nss, mm), denom));
-                                m8[k] = __float_as_uint(mm); v8[k] = __float_as_uint(vv); w8[k] = __float_as_uint(ww);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) o8[k] = pack_bf16(__uint_as_float(w8[2 * k]), __uint_as_float(w8[2 * k + 1]));
-                            st_global_256(pw + j, w8); st_global_256(pm + j, m8); st_global_256(pv + j, v8);
-                            *reinterpret_cast<uint4*>(pb + j) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
-                        }
-                    }
-                } else if (MODE == kRaw || MODE == kDw) {
+                if (MODE == kRaw || MODE == kDw) {
                     if (row_ok) {
                         float* dst = g.fout + (size_t)ks * g.fout_split + (size_t)b * g.fout_fit + g.fout_off + (size_t)row * g.ldf + col;
 #pragma unroll
@@ -513,20 +475,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (MODE == kDw && half == 0 && nt == 0) {
                 const uint32_t dbv = tmem_ld1(tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + BN);   // every column of the ones-product equals db[row]
                 tmem_ld_wait();
-                if (row_ok) {
-                    if (g.adam_epoch != nullptr) {
-                        const FitRec* rec = &g.recs[b];
-                        const size_t pi = (size_t)g.adam_b_off + row;
-                        const float gr = __uint_as_float(dbv);
-                        float mm = rec->m[pi], vv = rec->v[pi], ww = rec->params[pi];
-                        mm = __fadd_rn(mm, __fmul_rn(1.0f - g.adam_beta1, __fsub_rn(gr, mm)));
-                        vv = __fadd_rn(__fmul_rn(vv, g.adam_beta2), __fmul_rn(__fmul_rn(1.0f - g.adam_beta2, gr), gr));
-                        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), adam_bc2v), g.adam_eps);
-                        ww = __fadd_rn(ww, __fdiv_rn(__fmul_rn(adam_nss, mm), denom));
-                        rec->m[pi] = mm; rec->v[pi] = vv; rec->params[pi] = ww;
-                        if (g.adam_psc) g.adam_psc[(size_t)b * g.adam_psc_fit + g.adam_psc_off + row] = rec->omega * ww;
-                    } else g.biasgrad[(size_t)b * g.biasgrad_fit + (size_t)ks * g.M + row] = __uint_as_float(dbv);
-                }
+                if (row_ok) g.biasgrad[(size_t)b * g.biasgrad_fit + (size_t)ks * g.M + row] = __uint_as_float(dbv);
             }
             if (MODE == kFwdDot && row_ok)     // this thread's row, this warp's half of the tile's columns
                 g.dotpart[(size_t)b * g.dotpart_fit + (size_t)(nt * 2 + half) * g.M + row] = sq;

@@ -17,7 +17,9 @@ PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'bf16': PREC_BF16}
 
 _LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'libnerfattn.so'
+_PROF_LIB_PATH = _LIB_PATH.with_name('libnerfattn_prof.so')
 _lib = None
+_prof_lib = None
 
 c_void_p, c_int32, c_float, c_double, c_size_t = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_float,
                                                   ctypes.c_double, ctypes.c_size_t)
@@ -89,24 +91,37 @@ def library_path() -> Path:
     return Path(os.environ.get('NERFATTN_LIB', _LIB_PATH))
 
 
+def _load(path: Path) -> ctypes.CDLL:
+    if not path.exists():
+        raise NativeError(
+            f'{path} not found: build it with `python __graft_entry__.py` (or `make -C '
+            f'{path.parent}`); nerf_attention has no CPU / PyTorch fallback')
+    handle = ctypes.CDLL(str(path))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(handle, name)          # AttributeError if the .so is stale
+        fn.restype, fn.argtypes = res, args
+    got = handle.nerfattn_abi_version()
+    if got != ABI_VERSION:
+        raise NativeError(f'{path}: ABI version {got}, binding expects {ABI_VERSION}; rebuild')
+    return handle
+
+
 def lib() -> ctypes.CDLL:
     """Load (once) and type the shared library; raise loudly if it is not there."""
     global _lib
     if _lib is None:
-        path = library_path()
-        if not path.exists():
-            raise NativeError(
-                f'{path} not found: build it with `python __graft_entry__.py` (or `make -C '
-                f'{path.parent}`); nerf_attention has no CPU / PyTorch fallback')
-        handle = ctypes.CDLL(str(path))
-        for name, (res, args) in _SIGNATURES.items():
-            fn = getattr(handle, name)          # AttributeError if the .so is stale
-            fn.restype, fn.argtypes = res, args
-        got = handle.nerfattn_abi_version()
-        if got != ABI_VERSION:
-            raise NativeError(f'{path}: ABI version {got}, binding expects {ABI_VERSION}; rebuild')
-        _lib = handle
+        _lib = _load(library_path())
     return _lib
+
+
+def prof_lib() -> ctypes.CDLL:
+    """The -DNA_PROFILING build of the same sources (libnerfattn_prof.so): it honours NERFATTN_PHASE, which makes
+    a fit launch only one class of kernels per epoch.  For bench.py / profiles only -- nothing in the package
+    calls this, and results of a phase-masked run are meaningless."""
+    global _prof_lib
+    if _prof_lib is None:
+        _prof_lib = _load(_PROF_LIB_PATH)
+    return _prof_lib
 
 
 def check(rc: int, what: str) -> None:

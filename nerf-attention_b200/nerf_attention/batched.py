@@ -111,9 +111,9 @@ class FitBatch:
 
     def __init__(self, jobs: list[FitJob], epochs: int = 5000, lr: float = 1e-4, device: str = 'cuda',
                  precision: str | None = None, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 keep_initial: bool = False, progress_every: int = 0):
+                 keep_initial: bool = False, progress_every: int = 0, lib=None):
         self.dev = dev = _native.require_cuda(device)
-        self.lib = _native.lib()
+        self.lib = lib if lib is not None else _native.lib()      # `lib`: bench.py's profiling build
         self.prec = _native.precision_code(precision)
         self.jobs, self.epochs, self.betas, self.eps = jobs, epochs, betas, eps
         self.stats = stats = TransferStats()
