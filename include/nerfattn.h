@@ -47,15 +47,21 @@ enum {
     NA_ERR_CUDA = -4           /* a CUDA runtime / driver call failed                    */
 };
 
+/*
+ * Two precisions.  BASELINE.json's north_star allows "TF32/BF16" for the tensor mode; only BF16 is built:
+ * with fp32 accumulation, an fp32 layer 0 and fp32 master weights it stays within 1.6e-4 of the reference's
+ * final CosSim at the benched configuration (gate 5e-3; tests/test_gpu_full_length.py), at twice the tensor
+ * rate and half the operand bytes a kind::tf32 variant would have.  Code 1 is unassigned (NA_ERR_UNSUPPORTED).
+ */
 enum {
     NA_PREC_FP32 = 0,          /* SIMT fp32 FMA everywhere: the parity mode (1e-5 / 1e-3) */
-    NA_PREC_TF32 = 1,          /* reserved; currently NA_ERR_UNSUPPORTED                   */
     NA_PREC_BF16 = 2           /* tcgen05 BF16 x BF16 -> FP32 for the H->H / H->D layers;
                                   layer 0, loss, Adam and master weights stay fp32        */
 };
 
 enum {
-    NA_FIT_TARGETS_PRENORMALISED = 1   /* targets already (t-mean)/std; mean/std are inputs */
+    NA_FIT_TARGETS_PRENORMALISED = 1   /* targets already (t-mean)/std; mean/std are inputs (device, [D]); the
+                                          final metrics are computed against targets * std + mean */
 };
 
 /*

@@ -163,7 +163,15 @@ template <int N>
 __device__ __forceinline__ void sincos_group_mufu(const float (&x)[N], float (&s)[N], float (&c)[N]) {
     float big = 0.f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { mufu_sincos(x[i], s[i], c[i]); big = fmaxf(big, fabsf(x[i])); }
+    for (int i = 0; i < N; ++i) {
+        mufu_sincos(x[i], s[i], c[i]);
+#ifndef NA_EXP_NOBIG                       // sensitivity experiments (profiles/README.md): never defined in a product build
+        big = fmaxf(big, fabsf(x[i]));
+#endif
+#ifdef NA_EXP_HALFMUFU
+        c[i] = s[i];
+#endif
+    }
     if (big > kSincosFastLimit) {
 #pragma unroll
         for (int i = 0; i < N; ++i) { const float2 r = slow_sincos(x[i]); s[i] = r.x; c[i] = r.y; }

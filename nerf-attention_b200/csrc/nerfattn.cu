@@ -63,31 +63,27 @@ struct Group {
     __nv_bfloat16* wbf16;  // [nf][P] bf16 mirror of the weights (tensor path)
     tc::GroupMaps* maps;   // TMA descriptors (unfused tensor path), host-side
     // fused row-tile chain (siren_chain.cuh): forward + loss + dX chain in one kernel; cosb[l] then
-    // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch.  The group is trained in
-    // `nchunks` sub-batches of `chunk` fits that share ONE set of activation buffers (act / cosb / dy hold
-    // `chunk` fits): chain(c) -> dW + Adam(c) back to back, so that what the chain kernel stores is still
-    // in L2 when the dW kernel reads it, and the next sub-batch overwrites the same lines.
+    // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch
     bool use_chain;
-    int chunk, nchunks;
     __nv_bfloat16* chain_scratch;
     float* psc;            // omega-prescaled W0 / sine-layer biases [nf][(L+2)H]
-    std::vector<chain::ChainMaps> cmaps;   // per sub-batch (the weight maps start at the sub-batch's first fit)
+    chain::ChainMaps cmaps;
     dw::DwMaps dmaps;
     // layer-0 gradient operand (chain::xop_kernel): one table per distinct position vector of the group
     std::vector<const float*> pos_tabs; std::vector<int> posid;    // posid[k]: table of the group's k-th fit
     const float** d_pos_tabs; __nv_bfloat16* xop;
+    // every group counts its own epochs (the Adam kernel that ends a group's epoch increments the counter), so
+    // groups never wait for one another inside a multi-epoch graph
+    int* d_epoch; unsigned int* d_done;
 };
 
-// Fits per sub-batch of a chain group.  NERFATTN_CHUNK_MB (tuning): bf16 activation bytes per sub-batch.
-static int chain_chunk_fits(int N, int D, int H, int L, int nf) {
-    const char* e = getenv("NERFATTN_CHUNK_MB");
-    const double mb = e ? atof(e) : 0.0;
-    if (mb <= 0.0) return nf;
-    const double per_fit = ((double)2 * (L + 1) * N * H + (double)N * D) * 2.0;
-    int c = (int)(mb * 1e6 / per_fit);
-    c = std::max(1, std::min(c, nf));
-    const int n = ceil_div(nf, c);
-    return ceil_div(nf, n);                       // balanced sub-batches
+// A shape group larger than this is split into several groups ("units") with their own buffers: the two-lane
+// schedule (record_epochs) overlaps the HBM-bound dW + Adam kernel of one unit with the chain kernel of the next,
+// which needs more than a few units per epoch.  NERFATTN_UNIT_FITS overrides (0 = never split).
+static int unit_fits_cap() {
+    const char* e = getenv("NERFATTN_UNIT_FITS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : (1 << 30);
 }
 
 struct Plan {
@@ -98,7 +94,7 @@ struct Plan {
     std::vector<size_t> uniq_tnorm_off, uniq_stat_off;
     const float** d_uniq_ptr; int* d_uniq_prenorm;
     float* tnorm; float* ustat_mean; float* ustat_std;
-    int* d_epoch; float* d_step_size; float* d_bc2;
+    float* d_step_size; float* d_bc2;
     size_t bytes;
 };
 
@@ -127,15 +123,17 @@ static int validate(const na_fit_t* fits, int nfits, int precision) {
 // Lay the workspace out.  With ws == nullptr this only computes sizes.
 static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision, void* ws, Plan& plan) {
     Arena ar(ws);
-    std::map<std::tuple<int, int, int, int>, int> gid;
+    std::map<std::tuple<int, int, int, int>, int> gid;                 // shape -> the group currently being filled
+    const int cap = (precision == NA_PREC_BF16) ? unit_fits_cap() : (1 << 30);
     for (int i = 0; i < nfits; ++i) {
         auto key = std::make_tuple(fits[i].N, fits[i].D, fits[i].H, fits[i].L);
         auto it = gid.find(key);
-        if (it == gid.end()) {
+        if (it == gid.end() || (int)plan.groups[it->second].fit_idx.size() >= cap) {
             Group g{};
             g.N = fits[i].N; g.D = fits[i].D; g.H = fits[i].H; g.L = fits[i].L;
             g.lm = make_layer_map(g.H, g.L, g.D);
-            it = gid.emplace(key, (int)plan.groups.size()).first;
+            gid[key] = (int)plan.groups.size();
+            it = gid.find(key);
             plan.groups.push_back(g);
         }
         plan.groups[it->second].fit_idx.push_back(i);
@@ -165,7 +163,6 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
     plan.tnorm = ar.take<float>(tnorm_total);
     plan.ustat_mean = ar.take<float>(stat_total);
     plan.ustat_std = ar.take<float>(stat_total);
-    plan.d_epoch = ar.take<int>(64);
     plan.d_step_size = ar.take<float>(std::max(epochs, 1));
     plan.d_bc2 = ar.take<float>(std::max(epochs, 1));
 
@@ -176,16 +173,15 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         g.mtiles = ceil_div(g.N, 128);
         g.d_recs = ar.take<FitRec>(g.nf);
         g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
-        g.chunk = g.use_chain ? chain_chunk_fits(g.N, g.D, g.H, g.L, g.nf) : g.nf;
-        g.nchunks = ceil_div(g.nf, g.chunk);
+        g.d_epoch = ar.take<int>(64);
+        g.d_done = ar.take<unsigned int>(64);
         const size_t nh = (size_t)g.nf * g.N * g.H, nd = (size_t)g.nf * g.N * g.D;
-        const size_t ch = (size_t)g.chunk * g.N * g.H, cd = (size_t)g.chunk * g.N * g.D;     // one sub-batch
         for (int l = 0; l <= g.L; ++l) {
-            g.act[l] = ar.take<char>(ch * esz);
-            g.cosb[l] = ar.take<char>(ch * esz);
+            g.act[l] = ar.take<char>(nh * esz);
+            if (l > 0 || !g.use_chain) g.cosb[l] = ar.take<char>(nh * esz);          // chain: dz_0 never leaves the SM
         }
         if (!g.use_chain) { g.dz[0] = ar.take<char>(nh * esz); g.dz[1] = ar.take<char>(nh * esz); }
-        g.dy = ar.take<char>(cd * esz);
+        g.dy = ar.take<char>(nd * esz);
         g.yeval = ar.take<float>(nd);
         if (bf) { g.evalact[0] = ar.take<float>(nh); g.evalact[1] = ar.take<float>(nh); }
         // split-K of dW so that the launch fills the GPU: ~2 waves of CTAs on the fp32 path (partials summed by Adam);
@@ -293,7 +289,8 @@ static void launch_adam(const Group& g, const Plan& plan, double beta1, double b
                         bool layer0_only = false) {
     f32::AdamArgs a{};
     a.recs = g.d_recs; a.lm = g.lm;
-    a.et.epoch = plan.d_epoch; a.et.step_size = plan.d_step_size; a.et.bc2_sqrt = plan.d_bc2;
+    a.et.epoch = g.d_epoch; a.et.step_size = plan.d_step_size; a.et.bc2_sqrt = plan.d_bc2;
+    a.epoch_rw = g.d_epoch; a.done = g.d_done;            // the last block of this launch ends the group's epoch
     a.gradpart = g.gradpart; a.grad_split_stride = (size_t)g.nf * g.lm.P; a.grad_fit = g.lm.P; a.nsplit = g.nsplit;
     a.colpart = g.colpart;
     for (int l = 0; l < kMaxLayers; ++l) a.colpart_layer_off[l] = g.colpart_layer_off[l];
@@ -354,31 +351,31 @@ static void fp32_epoch(const Group& g, const Plan& plan, double b1, double b2, d
     launch_adam(g, plan, b1, b2, eps, s);
 }
 
-// one training epoch of one group on the fused chain path (BF16): per sub-batch the row-tile chain, the layer-0
-// gradient and the grouped dW + Adam kernel; then Adam of the 2H layer-0 parameters (it also writes losses[e])
-static int chain_epoch(const Group& g, const Plan& plan, double b1, double b2, double eps, cudaStream_t s) {
+// One training epoch of one group on the fused chain path (BF16) is three launches:
+//   chain_part   the row-tile chain (forward, loss, dX, layer-0 gradient partials)          -- FP32/SFU-issue-bound
+//   update_part  the grouped dW + Adam kernel, then Adam of the 2H layer-0 parameters (it also writes losses[e]
+//                and ends the group's epoch)                                                -- HBM-bound
+// max_ctas caps the persistent grids (0 = all SMs): the two-lane schedule runs the two halves of different groups
+// side by side on disjoint sets of SMs.
+static int chain_part(const Group& g, int max_ctas, cudaStream_t s) {
+    if (!(chain::phase_mask() & 1)) return NA_OK;
+    return chain::train_step(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, g.cmaps, g.chain_scratch, g.losspart,
+                             g.losspart_per_fit, g.mtiles, g.psc, g.xpart, g.colpart + g.colpart_layer_off[0], max_ctas, s);
+}
+static int update_part(const Group& g, const Plan& plan, double b1, double b2, double eps, int max_ctas, cudaStream_t s) {
     const int phases = chain::phase_mask();
-    const size_t pscf = chain::psc_floats(g.H, g.L);
-    dw::DwArgs da{};
-    dw::fill_args(da, g.N, g.D, g.H, g.L, g.lm);
-    da.epoch = plan.d_epoch; da.step_size = plan.d_step_size; da.bc2 = plan.d_bc2;
-    da.beta1 = (float)b1; da.beta2 = (float)b2; da.eps = (float)eps;
-    da.wbf16_fit = g.lm.P; da.psc_fit = pscf;
-    int rc;
-    for (int c = 0; c < g.nchunks; ++c) {
-        const int first = c * g.chunk, cnt = std::min(g.chunk, g.nf - first);
-        if ((phases & 1) &&
-            (rc = chain::train_step(g.N, g.D, g.H, g.L, cnt, g.lm, g.d_recs + first, g.cmaps[c], g.chain_scratch,
-                                    g.losspart + (size_t)first * g.losspart_per_fit, g.losspart_per_fit, g.mtiles,
-                                    g.psc + (size_t)first * pscf, g.xpart + (size_t)first * g.mtiles * g.H,
-                                    g.colpart + g.colpart_layer_off[0] + (size_t)first * g.mtiles * g.H, s))) return rc;
-        if (!(phases & 2)) continue;
-        da.nf = cnt; da.recs = g.d_recs + first;
-        da.wbf16 = g.wbf16 + (size_t)first * g.lm.P;
-        da.psc = g.psc + (size_t)first * pscf;
-        if ((rc = dw::launch(g.dmaps, da, s))) return rc;
+    if (phases & 2) {
+        dw::DwArgs da{};
+        dw::fill_args(da, g.N, g.D, g.H, g.L, g.lm);
+        da.epoch = g.d_epoch; da.step_size = plan.d_step_size; da.bc2 = plan.d_bc2;
+        da.beta1 = (float)b1; da.beta2 = (float)b2; da.eps = (float)eps;
+        da.nf = g.nf; da.recs = g.d_recs;
+        da.wbf16 = g.wbf16; da.wbf16_fit = g.lm.P;
+        da.psc = g.psc; da.psc_fit = chain::psc_floats(g.H, g.L);
+        int rc = dw::launch(g.dmaps, da, max_ctas, s);
+        if (rc) return rc;
     }
-    if (phases & 4) launch_adam(g, plan, b1, b2, eps, s, /*layer0_only=*/true);
+    launch_adam(g, plan, b1, b2, eps, s, /*layer0_only=*/true);      // always: it ends the epoch (profiling masks included)
     return NA_OK;
 }
 
@@ -429,18 +426,19 @@ static void reap_graphs() {
 struct CaptureKit {
     int device = -1;
     cudaStream_t cap = nullptr;
-    cudaEvent_t fork = nullptr;
-    std::vector<cudaStream_t> side;
-    std::vector<cudaEvent_t> joins;
-    bool grow(size_t nside) {
+    std::vector<cudaStream_t> streams;            // lanes / per-group branches
+    std::vector<cudaEvent_t> events;              // fork, joins, cross-lane dependencies
+    bool grow(size_t nstreams, size_t nevents) {
         if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) return false;
-        if (!fork && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
-        while (side.size() < nside) {
-            cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+        while (streams.size() < nstreams) {
+            cudaStream_t st = nullptr;
             if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return false;
-            side.push_back(st);
+            streams.push_back(st);
+        }
+        while (events.size() < nevents) {
+            cudaEvent_t ev = nullptr;
             if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
-            joins.push_back(ev);
+            events.push_back(ev);
         }
         return true;
     }
@@ -449,7 +447,7 @@ static std::mutex g_kit_mu;
 static std::vector<CaptureKit*> g_kits;          // idle kits of every device
 struct KitLease {
     CaptureKit* kit = nullptr;
-    explicit KitLease(size_t nside) {
+    KitLease(size_t nstreams, size_t nevents) {
         const int dev = tc::current_device();
         {
             std::lock_guard<std::mutex> lk(g_kit_mu);
@@ -457,7 +455,7 @@ struct KitLease {
                 if (g_kits[i]->device == dev) { kit = g_kits[i]; g_kits[i] = g_kits.back(); g_kits.pop_back(); break; }
         }
         if (!kit) { kit = new CaptureKit(); kit->device = dev; }
-        if (!kit->grow(nside)) {                  // leave what exists in the pool; the caller reports the CUDA error
+        if (!kit->grow(nstreams, nevents)) {                  // leave what exists in the pool; the caller reports the CUDA error
             std::lock_guard<std::mutex> lk(g_kit_mu);
             g_kits.push_back(kit);
             kit = nullptr;
@@ -505,10 +503,10 @@ extern "C" long long nerfattn_fit_launch_count(const na_fit_t* fits, int32_t nfi
     Plan plan{};
     make_plan(fits, nfits, 1, precision, nullptr, plan);
     long long setup = (long long)plan.uniq_ptr.size() /* <= one norm launch per tensor */ + plan.groups.size();
-    long long per_epoch = 1 /* tick */, fin = 0;
+    long long per_epoch = 0, fin = 0;
     for (const Group& g : plan.groups) {
         // layer0 + L fwd + out + (L+1) x (dW, dX) + Adam; the tensor path adds the layer-0 gradient kernel
-        if (g.use_chain) per_epoch += 2 * g.nchunks + 1;          // per sub-batch: chain, dW + Adam; then Adam of layer 0
+        if (g.use_chain) per_epoch += 3;                          // chain, dW + Adam, Adam of layer 0
         else per_epoch += 1 + g.L + 1 + 2 * (g.L + 1) + 1 + (precision == NA_PREC_BF16 ? 1 : 0);
         fin += 1 + g.L + 1 + 2;
         if (precision == NA_PREC_BF16) setup += 1;   // bf16 weight mirror
@@ -551,7 +549,10 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     // ---- host tables -> device
     NA_CUDA_OK(cudaMemcpyAsync(plan.d_uniq_ptr, plan.uniq_ptr.data(), nu * sizeof(float*), cudaMemcpyHostToDevice, stream));
     NA_CUDA_OK(cudaMemcpyAsync(plan.d_uniq_prenorm, plan.uniq_prenorm.data(), nu * sizeof(int), cudaMemcpyHostToDevice, stream));
-    NA_CUDA_OK(cudaMemsetAsync(plan.d_epoch, 0, sizeof(int), stream));
+    for (Group& g : plan.groups) {
+        NA_CUDA_OK(cudaMemsetAsync(g.d_epoch, 0, sizeof(int), stream));
+        NA_CUDA_OK(cudaMemsetAsync(g.d_done, 0, sizeof(unsigned int), stream));
+    }
     if (epochs > 0) {
         std::vector<float> ss(epochs), bc2(epochs);
         for (int e = 0; e < epochs; ++e) {          // torch/optim/adam.py: python-float (double) math
@@ -635,17 +636,13 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
         for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
             Group& g = plan.groups[gi];
             if (g.use_chain) {
-                g.cmaps.resize(g.nchunks);
-                for (int c = 0; c < g.nchunks; ++c) {
-                    const int first = c * g.chunk, cnt = std::min(g.chunk, g.nf - first);
-                    if ((rc = chain::build_maps(g.N, g.D, g.H, g.L, cnt, g.lm, g.wbf16 + (size_t)first * g.lm.P, g.act, g.cosb,
-                                                g.dy, g.xop, g.mtiles * (int)g.pos_tabs.size(), g.cmaps[c]))) return rc;
-                }
+                if ((rc = chain::build_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.wbf16, g.act, g.cosb, g.dy, g.xop,
+                                            g.mtiles * (int)g.pos_tabs.size(), g.cmaps))) return rc;
                 NA_CUDA_OK(cudaMemcpyAsync(g.d_pos_tabs, g.pos_tabs.data(), g.pos_tabs.size() * sizeof(float*),
                                            cudaMemcpyHostToDevice, stream));
                 chain::xop_kernel<<<dim3(g.mtiles, (unsigned)g.pos_tabs.size()), tc::BM, 0, stream>>>(g.d_pos_tabs, g.N, g.mtiles, g.xop);
                 NA_LAUNCH_OK("xop_kernel");
-                if ((rc = dw::build_maps(g.N, g.D, g.H, g.L, g.chunk, g.act, g.cosb, g.dy, g.dmaps))) return rc;
+                if ((rc = dw::build_maps(g.N, g.D, g.H, g.L, g.nf, g.act, g.cosb, g.dy, g.dmaps))) return rc;
             } else {
                 g.maps = &maps[gi];
                 if ((rc = tc::build_group_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.act, g.cosb, g.dz, g.dy, g.wbf16, *g.maps)))
@@ -658,28 +655,75 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     }
 
     // ---- epoch loop
-    auto record_epoch = [&](cudaStream_t main, std::vector<cudaStream_t>& side, cudaEvent_t fork,
-                            std::vector<cudaEvent_t>& joins) -> int {
-        const bool parallel = !side.empty();
-        if (parallel) cudaEventRecord(fork, main);
-        for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
-            cudaStream_t s = parallel ? side[gi] : main;
-            if (parallel) cudaStreamWaitEvent(s, fork, 0);
-            const Group& g = plan.groups[gi];
-            if (precision == NA_PREC_FP32) fp32_epoch(g, plan, beta1, beta2, eps, s);
-            else if (g.use_chain) {
-                int r2 = chain_epoch(g, plan, beta1, beta2, eps, s);
-                if (r2) return r2;
-            } else {
-                int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy,
-                                   g.gradpart, g.colpart, g.colpart_layer_off, g.xpart, g.losspart,
-                                   g.losspart_per_fit, g.mtiles, s);
-                if (r2) return r2;
-                launch_adam(g, plan, beta1, beta2, eps, s);
-            }
-            if (parallel) { cudaEventRecord(joins[gi], s); cudaStreamWaitEvent(main, joins[gi], 0); }
+    // One epoch of one group, all of it on stream s (eager mode, fp32, unfused tensor path, single-group calls).
+    auto group_epoch = [&](const Group& g, cudaStream_t s) -> int {
+        if (precision == NA_PREC_FP32) { fp32_epoch(g, plan, beta1, beta2, eps, s); return NA_OK; }
+        if (g.use_chain) {
+            int r2 = chain_part(g, 0, s);
+            return r2 ? r2 : update_part(g, plan, beta1, beta2, eps, 0, s);
         }
-        f32::tick_kernel<<<1, 32, 0, main>>>(plan.d_epoch);
+        int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy, g.gradpart,
+                           g.colpart, g.colpart_layer_off, g.xpart, g.losspart, g.losspart_per_fit, g.mtiles, s);
+        if (r2) return r2;
+        launch_adam(g, plan, beta1, beta2, eps, s);
+        return NA_OK;
+    };
+    const size_t ng = plan.groups.size();
+    // Two-lane schedule of the chain path (all groups on it, at least two of them): the chain kernels of all groups run
+    // back to back on the "compute lane" with grid_c persistent CTAs, each group's dW + Adam follows on the "memory
+    // lane" with the remaining SMs while the next group's chain kernel runs -- the chain is FP32/SFU-issue-bound with
+    // HBM to spare, dW + Adam is HBM-bound with the SMs idle, and neither can share an SM with the other (shared memory).
+    // Every group counts its own epochs, so inside a multi-epoch graph a group's next chain kernel only waits for that
+    // group's own Adam.  NERFATTN_LANES = CTAs of the compute lane; default 0 = off (one branch per group, full grids):
+    // measured on B200 (profiles/README.md, round 2) the schedule LOSES -- 1.75 ms per epoch at 108 + 40 CTAs against
+    // 1.67 ms without it -- because the dW + Adam kernel is bound by the load latency of each SM (128 KB of operand
+    // stages + the Adam stream in flight per SM), so its time grows as 148 / grid_m (0.54 -> 1.29 ms on 40 SMs) and
+    // the memory lane becomes the bottleneck; the SM-time of the two halves is conserved.
+    bool all_chain = precision == NA_PREC_BF16;
+    for (const Group& g : plan.groups) all_chain = all_chain && g.use_chain;
+    int grid_c = 0;
+    { const char* e = getenv("NERFATTN_LANES"); if (e) grid_c = atoi(e); }
+    grid_c &= ~1;                                           // CTA pairs
+    const int sms = tc::num_sms();
+    const bool lanes = all_chain && ng >= 2 && grid_c >= 2 && grid_c <= sms - 8;
+    const int grid_m = sms - grid_c;
+
+    // Enqueue `count` epochs of every group behind whatever is on `main`; with a kit (stream capture) the groups fan out.
+    auto record_epochs = [&](int count, cudaStream_t main, CaptureKit* kit) -> int {
+        int r2 = NA_OK;
+        if (!kit || ng == 1) {
+            for (int e = 0; e < count && !r2; ++e)
+                for (size_t gi = 0; gi < ng && !r2; ++gi) r2 = group_epoch(plan.groups[gi], main);
+        } else if (lanes) {
+            cudaStream_t lc = kit->streams[0], lm = kit->streams[1];
+            cudaEvent_t* ev = kit->events.data();            // [0] fork, [1] [2] joins, [3 + 2g] chain done, [4 + 2g] Adam done
+            cudaEventRecord(ev[0], main);
+            cudaStreamWaitEvent(lc, ev[0], 0);
+            cudaStreamWaitEvent(lm, ev[0], 0);
+            for (int e = 0; e < count && !r2; ++e)
+                for (size_t gi = 0; gi < ng && !r2; ++gi) {
+                    const Group& g = plan.groups[gi];
+                    if (e > 0) cudaStreamWaitEvent(lc, ev[4 + 2 * gi], 0);       // this group's previous epoch has ended
+                    if ((r2 = chain_part(g, grid_c, lc))) break;
+                    cudaEventRecord(ev[3 + 2 * gi], lc);
+                    cudaStreamWaitEvent(lm, ev[3 + 2 * gi], 0);
+                    if ((r2 = update_part(g, plan, beta1, beta2, eps, grid_m, lm))) break;
+                    cudaEventRecord(ev[4 + 2 * gi], lm);
+                }
+            cudaEventRecord(ev[1], lc); cudaStreamWaitEvent(main, ev[1], 0);
+            cudaEventRecord(ev[2], lm); cudaStreamWaitEvent(main, ev[2], 0);
+        } else {
+            cudaEvent_t* ev = kit->events.data();            // [0] fork, [1 + g] joins
+            cudaEventRecord(ev[0], main);
+            for (size_t gi = 0; gi < ng; ++gi) {
+                cudaStream_t sg = kit->streams[gi];
+                cudaStreamWaitEvent(sg, ev[0], 0);
+                for (int e = 0; e < count && !r2; ++e) r2 = group_epoch(plan.groups[gi], sg);
+                cudaEventRecord(ev[1 + gi], sg);
+                cudaStreamWaitEvent(main, ev[1 + gi], 0);
+            }
+        }
+        if (r2) return r2;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("epoch launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
         return NA_OK;
@@ -696,36 +740,50 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
         }
         return NA_OK;
     };
+    const bool logging = log_every > 0 && progress;
 
     if (epochs > 0) {
-        const bool use_graph = !env_flag("NERFATTN_NO_GRAPH");
-        if (use_graph) {
-            const size_t nside = plan.groups.size() > 1 ? plan.groups.size() : 0;
-            KitLease lease(nside);
+        if (!env_flag("NERFATTN_NO_GRAPH")) {
+            // Graphs of up to `glen` epochs (NERFATTN_GRAPH_EPOCHS), replayed; a shorter one covers remainders and the
+            // stretches between progress evaluations.  Replays are stream-ordered, so the lanes drain once per replay.
+            int glen = 20;
+            { const char* e = getenv("NERFATTN_GRAPH_EPOCHS"); if (e && atoi(e) > 0) glen = atoi(e); }
+            KitLease lease(lanes ? 2 : ng, lanes ? 3 + 2 * ng : 1 + ng);
             if (!lease.kit) { set_error("cannot create capture streams / events: %s", cudaGetErrorString(cudaGetLastError())); return NA_ERR_CUDA; }
-            std::vector<cudaStream_t> side(lease.kit->side.begin(), lease.kit->side.begin() + nside);
-            std::vector<cudaEvent_t> joins(lease.kit->joins.begin(), lease.kit->joins.begin() + nside);
-            GraphHold gh;
-            NA_CUDA_OK(cudaStreamBeginCapture(lease.kit->cap, cudaStreamCaptureModeThreadLocal));
-            rc = record_epoch(lease.kit->cap, side, lease.kit->fork, joins);
-            cudaError_t ce = cudaStreamEndCapture(lease.kit->cap, &gh.graph);      // always ends the capture, also after an error
-            if (rc) return rc;
-            if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
-            ce = cudaGraphInstantiate(&gh.exec, gh.graph, 0);
-            if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
-            for (int e = 0; e < epochs; ++e) {
+            std::map<int, GraphHold> graphs;                  // by length; destroyed on every early return
+            auto graph_of = [&](int len, cudaGraphExec_t* out) -> int {
+                GraphHold& gh = graphs[len];
+                if (!gh.exec) {
+                    NA_CUDA_OK(cudaStreamBeginCapture(lease.kit->cap, cudaStreamCaptureModeThreadLocal));
+                    const int r2 = record_epochs(len, lease.kit->cap, lease.kit);
+                    cudaError_t ce = cudaStreamEndCapture(lease.kit->cap, &gh.graph);   // always ends the capture, also after an error
+                    if (r2) return r2;
+                    if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
+                    ce = cudaGraphInstantiate(&gh.exec, gh.graph, 0);
+                    if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
+                }
+                *out = gh.exec;
+                return NA_OK;
+            };
+            for (int e = 0; e < epochs;) {
                 if ((rc = log_progress(e))) return rc;
-                ce = cudaGraphLaunch(gh.exec, stream);
+                int len = std::min(glen, epochs - e);
+                if (logging) len = std::min(len, log_every - ((e + 1) % log_every));   // stop before the next evaluation point
+                len = std::max(len, 1);
+                cudaGraphExec_t exec = nullptr;
+                if ((rc = graph_of(len, &exec))) return rc;
+                cudaError_t ce = cudaGraphLaunch(exec, stream);
                 if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
+                e += len;
             }
-            park_graph(gh.exec, gh.graph, stream);          // still running: destroyed by a later call
-            gh.release();
+            for (auto& kv : graphs) {                        // still running: destroyed by a later call
+                if (kv.second.exec) park_graph(kv.second.exec, kv.second.graph, stream);
+                kv.second.release();
+            }
         } else {
-            std::vector<cudaStream_t> none; std::vector<cudaEvent_t> nonej;
             for (int e = 0; e < epochs; ++e) {
                 if ((rc = log_progress(e))) return rc;
-                rc = record_epoch(stream, none, nullptr, nonej);
-                if (rc) return rc;
+                if ((rc = record_epochs(1, stream, nullptr))) return rc;
             }
         }
     }
@@ -928,9 +986,14 @@ extern "C" int nerfattn_kvread_qk(const void* k_fp16, const void* q_fp16, float*
     if (D != 64 && D != 128 && D != 256) { set_error("kvread: D must be 64, 128 or 256"); return NA_ERR_UNSUPPORTED; }
     const long long rows = (long long)n * N;
     const int G = D / 16;                                        // lanes per row, 32 B each
-    const long long groups_needed = (rows + 7) / 8;
+    const long long groups_needed = (rows + 3) / 4;             // 4 rows per lane group and batch
     long long blocks = (groups_needed * G + 255) / 256;
-    const long long cap = (long long)tc::num_sms() * 8;         // 8 resident CTAs of 256 threads per SM
+    // persistent grid: as many CTAs as are resident at once (registers: two batches of 4 x 32 B in flight per thread)
+    int occ = 0;
+    if (G == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dec::kvread_qk_kernel<4>, 256, 0);
+    else if (G == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dec::kvread_qk_kernel<8>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dec::kvread_qk_kernel<16>, 256, 0);
+    const long long cap = (long long)tc::num_sms() * std::max(occ, 1);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const uint32_t* K = (const uint32_t*)k_fp16; const uint32_t* q = (const uint32_t*)q_fp16;

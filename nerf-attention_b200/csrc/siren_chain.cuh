@@ -683,7 +683,9 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         }
                         if (!(FWD && s == L)) {
                             act_store16(act_u32, r, col0 + u * 16, so);
+#ifndef NA_EXP_NOSCRATCH
                             if (!FWD) st_global_256_hint(cdst + u * SCR_U, co, pol_keep);
+#endif
                         } else if (MODE == 2) {
                             // sum the 16 columns over the 32 rows of this warp: transpose-reduce, 16 shuffles
                             float w8[8], w4[4], w2[2];
@@ -798,8 +800,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     } else {
                     const __nv_bfloat16* csrc = scr + (size_t)lp * (BM * H);
                     uint32_t cc[PFD][8];
+#ifdef NA_EXP_NOSCRATCH
+#define NA_LD_COS(dst, src) do { for (int z_ = 0; z_ < 8; ++z_) (dst)[z_] = 0x3f003f00u + (uint32_t)lane; } while (0)
+#else
+#define NA_LD_COS(dst, src) ld_global_256_hint(src, dst, pol_keep)
+#endif
 #pragma unroll
-                    for (int p = 0; p < PFD; ++p) ld_global_256_hint(csrc + p * SCR_U, cc[p], pol_keep);
+                    for (int p = 0; p < PFD; ++p) NA_LD_COS(cc[p], csrc + p * SCR_U);
                     NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
                     if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
                     NA_T1();
@@ -819,7 +826,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * c0),
                                                 __uint_as_float(v[2 * t + 1]) * (omega * c1));
                         }
-                        if (u + PFD < NU) ld_global_256_hint(csrc + (u + PFD) * SCR_U, cc[u % PFD], pol_keep);
+                        if (u + PFD < NU) NA_LD_COS(cc[u % PFD], csrc + (u + PFD) * SCR_U);
                         act_store16(act_u32, r, col0 + u * 16, dout);
                     }
                     }
@@ -914,7 +921,8 @@ inline int build_maps(int N, int D, int H, int L, int nf, const LayerMap& lm, __
     if ((rc = make_map(&m.xop, xop, BM, XOP_N, xop_tiles, BM, (uint64_t)XOP_N * BM, 64, XOP_N))) return rc;
     for (int l = 0; l <= L; ++l) {
         if ((rc = make_operand_map(&m.hout[l], act[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
-        if ((rc = make_operand_map(&m.zout[l], dzs[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
+        // dz_0 is consumed on the SM (layer-0 gradient MMA): never stored, no map
+        if (l > 0 && (rc = make_operand_map(&m.zout[l], dzs[l], N, H, nf, (size_t)N * H, false, BM))) return rc;
     }
     if ((rc = make_operand_map(&m.yout, dy, N, D, nf, (size_t)N * D, false, BM))) return rc;
     for (int l = 1; l <= L + 1; ++l) {
@@ -944,10 +952,10 @@ inline cudaError_t launch_mode(int mode, int grid, const ChainMaps& maps, const 
 }
 // mode: 0 training, 1 decode logits, 2 decode values.  The 2-CTA cluster variant exists for training only.
 template <int H>
-inline int launch_h(const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s) {
+inline int launch_h(const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s, int max_ctas = 0) {
     const int tiles = a.nf * a.mtiles;
     const bool cl = mode == 0 && use_cluster(a.N, H, a.D);
-    int grid = std::min(tiles, num_sms());
+    int grid = std::min(tiles, (max_ctas > 0) ? std::min(max_ctas, num_sms()) : num_sms());
     if (cl) grid &= ~1;
     cudaError_t e;
     constexpr int NSD = (H <= 256) ? 2 : 1;                  // default slots
@@ -959,12 +967,12 @@ inline int launch_h(const ChainMaps& maps, const ChainArgs& a, int mode, cudaStr
     if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
 }
-inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s) {
+inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s, int max_ctas = 0) {
     switch (H) {
-        case 64: return launch_h<64>(maps, a, mode, s);
-        case 128: return launch_h<128>(maps, a, mode, s);
-        case 256: return launch_h<256>(maps, a, mode, s);
-        case 512: return launch_h<512>(maps, a, mode, s);
+        case 64: return launch_h<64>(maps, a, mode, s, max_ctas);
+        case 128: return launch_h<128>(maps, a, mode, s, max_ctas);
+        case 256: return launch_h<256>(maps, a, mode, s, max_ctas);
+        case 512: return launch_h<512>(maps, a, mode, s, max_ctas);
         default: set_error("chain: unsupported H %d", H); return NA_ERR_UNSUPPORTED;
     }
 }
@@ -1014,7 +1022,7 @@ inline void scale_params(const FitRec* recs, int n, int H, int L, float* psc, cu
 // The weight gradients and Adam follow in dw::dw_adam_kernel (siren_dw.cuh), the layer-0 parameters in adam_kernel.
 inline int train_step(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
                       __nv_bfloat16* scratch, float* losspart, int losspart_per_fit, int mtiles, const float* psc,
-                      float* xpart, float* colpart0, cudaStream_t s) {
+                      float* xpart, float* colpart0, int max_ctas, cudaStream_t s) {
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
@@ -1025,7 +1033,7 @@ inline int train_step(int N, int D, int H, int L, int nf, const LayerMap& lm, co
     a.psc = psc; a.psc_fit = (int)psc_floats(H, L);
     a.xpart = xpart; a.colpart0 = colpart0;
     a.dbg = chain_dbg();
-    return launch(H, cm, a, 0, s);
+    return launch(H, cm, a, 0, s, max_ctas);
 }
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).

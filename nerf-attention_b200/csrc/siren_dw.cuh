@@ -280,9 +280,9 @@ inline void fill_args(DwArgs& a, int N, int D, int H, int L, const LayerMap& lm)
     (void)D;
 }
 
-inline int launch(const DwMaps& maps, const DwArgs& a, cudaStream_t s) {
+inline int launch(const DwMaps& maps, const DwArgs& a, int max_ctas, cudaStream_t s) {
     const int tiles = a.nf * a.tiles_per_fit;
-    const int grid = std::min(tiles, num_sms());
+    const int grid = std::min(tiles, (max_ctas > 0) ? std::min(max_ctas, num_sms()) : num_sms());
     if (bn_for(a.H) == 128) dw_adam_kernel<128><<<grid, NTHREADS, Cfg<128>::SMEM, s>>>(maps, a);
     else dw_adam_kernel<64><<<grid, NTHREADS, Cfg<64>::SMEM, s>>>(maps, a);
     cudaError_t e = cudaGetLastError();

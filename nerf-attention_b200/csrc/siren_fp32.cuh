@@ -402,7 +402,8 @@ struct AdamArgs {
     // BF16 copies of the hidden/output weights for the tensor path (nullptr in fp32 mode)
     __nv_bfloat16* wbf16; size_t wbf16_fit;
     float* psc; size_t psc_fit; int H, L;   // chain mode: omega-prescaled copies of W0 / the sine-layer biases to refresh
-    int p_end;              // parameters [0, p_end) are updated here (the rest in the dW epilogues when fused)
+    int p_end;              // parameters [0, p_end) are updated here (the rest in the fused dW + Adam kernel, siren_dw.cuh)
+    int* epoch_rw; unsigned int* done;   // the last block to finish increments the group's epoch counter (done: arrival count)
 };
 
 // One parameter of torch _single_tensor_adam (non-capturable branch), in torch's operation order and with IEEE
@@ -427,52 +428,62 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
         for (int i = 0; i < a.losspart_per_fit; ++i) s += a.losspart[(size_t)f * a.losspart_per_fit + i];
         rec.losses[e] = s * a.loss_inv_count;
     }
-    if (p >= a.p_end) return;
-
-    // which layer / weight-or-bias does p belong to
-    int layer = 0;
+    if (p < a.p_end) {
+        // which layer / weight-or-bias does p belong to
+        int layer = 0;
 #pragma unroll
-    for (int i = 1; i < kMaxLayers; ++i)
-        if (i < a.lm.nlayers && p >= a.lm.w_off[i]) layer = i;
-    const bool is_bias = p >= a.lm.b_off[layer];
-    const int width = a.lm.out_dim[layer];
+        for (int i = 1; i < kMaxLayers; ++i)
+            if (i < a.lm.nlayers && p >= a.lm.w_off[i]) layer = i;
+        const bool is_bias = p >= a.lm.b_off[layer];
+        const int width = a.lm.out_dim[layer];
 
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (is_bias || layer == 0) {
-        const int j = is_bias ? p - a.lm.b_off[layer] : p;
-        const int mt = is_bias ? a.col_mt[layer] : a.col_mt[0];
-        const float* src = (is_bias ? a.colpart + a.colpart_layer_off[layer] : a.xpart) + (size_t)f * mt * width + j;
-        for (int t = 0; t < mt; ++t) {
-            const float4 v = ldg4(src + (size_t)t * width);
-            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (is_bias || layer == 0) {
+            const int j = is_bias ? p - a.lm.b_off[layer] : p;
+            const int mt = is_bias ? a.col_mt[layer] : a.col_mt[0];
+            const float* src = (is_bias ? a.colpart + a.colpart_layer_off[layer] : a.xpart) + (size_t)f * mt * width + j;
+            for (int t = 0; t < mt; ++t) {
+                const float4 v = ldg4(src + (size_t)t * width);
+                g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+            }
+        } else {
+            const float* src = a.gradpart + (size_t)f * a.grad_fit + p;
+            for (int s = 0; s < a.nsplit; ++s) {
+                const float4 v = ldg4(src + (size_t)s * a.grad_split_stride);
+                g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+            }
         }
-    } else {
-        const float* src = a.gradpart + (size_t)f * a.grad_fit + p;
-        for (int s = 0; s < a.nsplit; ++s) {
-            const float4 v = ldg4(src + (size_t)s * a.grad_split_stride);
-            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+
+        // torch _single_tensor_adam: lerp, mul+addcmul, sqrt/bc2_sqrt + eps, addcdiv(value=-step_size)
+        const float4 m4 = *reinterpret_cast<const float4*>(rec.m + p), v4 = *reinterpret_cast<const float4*>(rec.v + p);
+        const float4 w4 = *reinterpret_cast<const float4*>(rec.params + p);
+        const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+        float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float bc2 = a.et.bc2_sqrt[e], nss = -a.et.step_size[e];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) adam_update(gs[i], m[i], v[i], w[i], 1.0f - a.beta1, a.beta2, 1.0f - a.beta2, a.eps, bc2, nss);
+        *reinterpret_cast<float4*>(rec.m + p) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(rec.v + p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(rec.params + p) = make_float4(w[0], w[1], w[2], w[3]);
+        if (a.psc && (layer == 0 || (is_bias && layer <= a.L))) {       // what the chain kernel's sine arguments read
+            float* dst = a.psc + (size_t)f * a.psc_fit + (layer == 0 ? p : (layer + 1) * a.H + (p - a.lm.b_off[layer]));
+            *reinterpret_cast<float4*>(dst) = make_float4(rec.omega * w[0], rec.omega * w[1], rec.omega * w[2], rec.omega * w[3]);
+        }
+        if (a.wbf16 && layer >= 1 && !is_bias) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
+            *reinterpret_cast<uint2*>(a.wbf16 + (size_t)f * a.wbf16_fit + p) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
         }
     }
-
-    // torch _single_tensor_adam: lerp, mul+addcmul, sqrt/bc2_sqrt + eps, addcdiv(value=-step_size)
-    const float4 m4 = *reinterpret_cast<const float4*>(rec.m + p), v4 = *reinterpret_cast<const float4*>(rec.v + p);
-    const float4 w4 = *reinterpret_cast<const float4*>(rec.params + p);
-    const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
-    float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
-    const float bc2 = a.et.bc2_sqrt[e], nss = -a.et.step_size[e];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) adam_update(gs[i], m[i], v[i], w[i], 1.0f - a.beta1, a.beta2, 1.0f - a.beta2, a.eps, bc2, nss);
-    *reinterpret_cast<float4*>(rec.m + p) = make_float4(m[0], m[1], m[2], m[3]);
-    *reinterpret_cast<float4*>(rec.v + p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(rec.params + p) = make_float4(w[0], w[1], w[2], w[3]);
-    if (a.psc && (layer == 0 || (is_bias && layer <= a.L))) {       // what the chain kernel's sine arguments read
-        float* dst = a.psc + (size_t)f * a.psc_fit + (layer == 0 ? p : (layer + 1) * a.H + (p - a.lm.b_off[layer]));
-        *reinterpret_cast<float4*>(dst) = make_float4(rec.omega * w[0], rec.omega * w[1], rec.omega * w[2], rec.omega * w[3]);
-    }
-    if (a.wbf16 && layer >= 1 && !is_bias) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
-        *reinterpret_cast<uint2*>(a.wbf16 + (size_t)f * a.wbf16_fit + p) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    // End of this group's epoch: every thread of the launch has read `e` by the time its block arrives here, so the
+    // last block to arrive may advance the counter (and re-arm the arrival count for the next launch).
+    if (a.done) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int nblocks = gridDim.x * gridDim.y;
+            if (atomicAdd(a.done, 1u) == nblocks - 1) { *a.done = 0u; *a.epoch_rw = e + 1; }
+        }
     }
 }
 
@@ -484,7 +495,6 @@ __global__ void progress_copy_kernel(const FitRec* recs, int nf, float* progress
     progress[2 * recs[k].fit_index + 1] = recs[k].scalars[1];
 }
 
-__global__ void tick_kernel(int* epoch) { if (threadIdx.x == 0) *epoch += 1; }
 
 // ---------------------------------------------------------------------------
 // final metrics (siren.py:119-125): one warp per row, then one block per fit.

@@ -1,8 +1,9 @@
 """B200-native drop-in for the SIREN fit / reconstruction path of ruskaruma/nerf-attention.
 
-Same import surface as the reference package for everything on that path
-(reference nerf_attention/__init__.py:1-21), including the structure analysis (batched torch
-operations, no figures); plotting entry points are not part of this build.
+Same import surface as the reference package (reference nerf_attention/__init__.py:1-21).  Limits: there is no CPU
+path (``device='cpu'`` raises; the reference falls back to the CPU); ``extract_kv_cache`` (real-LLM extraction) and the
+three figure functions ``plot_pareto_frontier`` / ``plot_keys_vs_values`` / ``generate_summary_figure`` import but raise
+NotImplementedError -- they are outside the hot path ("out of scope").
 """
 
 from nerf_attention.types import (
@@ -20,8 +21,11 @@ from nerf_attention.batched import FitJob, fit_many
 from nerf_attention.extract import extract_kv_cache, extract_kv_cache_synthetic
 from nerf_attention.fit import fit_kv_cache
 from nerf_attention.evaluate import (
+    generate_summary_figure,
     load_results,
     per_position_cosine,
+    plot_keys_vs_values,
+    plot_pareto_frontier,
     plot_per_position_error,
     profile_decode,
     profile_latency,
@@ -33,5 +37,5 @@ __all__ = [
     'SIREN', 'SineLayer', 'fit_siren', 'FitJob', 'fit_many',
     'extract_kv_cache', 'extract_kv_cache_synthetic', 'fit_kv_cache',
     'load_results', 'per_position_cosine', 'plot_per_position_error', 'profile_decode',
-    'profile_latency',
+    'profile_latency', 'plot_pareto_frontier', 'plot_keys_vs_values', 'generate_summary_figure',
 ]

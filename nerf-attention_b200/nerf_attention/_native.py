@@ -13,8 +13,9 @@ from pathlib import Path
 
 ABI_VERSION = 8
 
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
-PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'bf16': PREC_BF16}
+PREC_FP32, PREC_BF16 = 0, 2          # include/nerfattn.h: code 1 (a TF32 variant) is unassigned
+PRECISIONS = {'fp32': PREC_FP32, 'bf16': PREC_BF16}
+FIT_TARGETS_PRENORMALISED = 1        # na_fit_t.flags
 
 _LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'libnerfattn.so'
 _PROF_LIB_PATH = _LIB_PATH.with_name('libnerfattn_prof.so')

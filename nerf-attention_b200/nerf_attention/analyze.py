@@ -98,7 +98,8 @@ def analyze_tensor(tensor: torch.Tensor, name: str, max_lag: int = 50, device=No
         'lag1_autocorrelation': float(mean_autocorr[1].item()) if len(mean_autocorr) > 1 else 0.0,
         'mean_autocorrelation': mean_autocorr.tolist(),
         'spectral_energy': energy,
-        'rank': _effective_rank(full),
+        'rank': _effective_rank(tensor.detach().to(dev, torch.float32)),     # fp32 SVD like the reference (analyze.py:48-49): the
+        # 99 % threshold counts singular values, so the precision of the factorisation can move the rank by one
     }
 
 

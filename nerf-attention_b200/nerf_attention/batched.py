@@ -33,6 +33,10 @@ class FitJob:
     config: SIRENConfig
     model: SIREN | None = None              # pre-built (seeded) model; built in job order if None
     name: str = ''
+    # Optional: kv_tensor is ALREADY (t - mean) / std and these are the statistics (NA_FIT_TARGETS_PRENORMALISED):
+    # the library skips its normalisation pass and reports the final metrics against kv_tensor * std + mean.
+    target_mean: torch.Tensor | None = None  # [d_head] or [1, d_head]
+    target_std: torch.Tensor | None = None
 
 
 @dataclass
@@ -167,13 +171,20 @@ class FitBatch:
             self.scal = _Packer([8] * len(jobs), dev)
             self.mean = _Packer(dh, dev)
             self.std = _Packer(dh, dev)
+            for i, job in enumerate(jobs):                     # pre-normalised targets bring their statistics along
+                if (job.target_mean is None) != (job.target_std is None):
+                    raise ValueError('target_mean and target_std must be given together')
+                if job.target_mean is not None:
+                    self.mean.view(i, dh[i]).copy_(job.target_mean.reshape(-1).float(), non_blocking=True)
+                    self.std.view(i, dh[i]).copy_(job.target_std.reshape(-1).float(), non_blocking=True)
+                    stats.h2d_bytes += 8 * dh[i]
 
             self.fits = fits = (_native.NaFit * len(jobs))()
             for i, job in enumerate(jobs):
                 f = fits[i]
                 f.N, f.D = seq[i], dh[i]
                 f.H, f.L = job.config.hidden_features, job.config.hidden_layers
-                f.omega0, f.flags = job.config.omega_0, 0
+                f.omega0, f.flags = job.config.omega_0, (_native.FIT_TARGETS_PRENORMALISED if job.target_mean is not None else 0)
                 f.positions, f.targets = self.positions[i].data_ptr(), self.targets[i].data_ptr()
                 f.mean, f.std = self.mean.ptr(i), self.std.ptr(i)
                 f.params, f.adam_m, f.adam_v = params.ptr(i), self.adam_m.ptr(i), self.adam_v.ptr(i)

@@ -29,6 +29,7 @@ from nerf_attention.batched import FitJob, fit_many
 from nerf_attention.evaluate import PackedModels, _load_model_from_checkpoint, _time_cuda, kvread_qk
 from nerf_attention.analyze import _select_layers, analyze_kv_cache
 from nerf_attention.extract import extract_kv_cache_synthetic
+from nerf_attention.fit import detached_state
 from nerf_attention.types import KVMetadata, SIRENConfig
 
 MEDIUM = SIRENConfig(256, 2, 30.0, 'medium')
@@ -40,7 +41,7 @@ def _save_scaling_checkpoint(path: Path, name: str, result, seq_len: int) -> Non
     torch.save({
         'config': {'hidden_features': cfg.hidden_features, 'hidden_layers': cfg.hidden_layers,
                    'omega_0': cfg.omega_0, 'name': cfg.name, 'out_features': result.d_head},
-        'model_state': result.model.state_dict(),
+        'model_state': detached_state(result.model),      # copies, not views of the whole batch buffer
         'target_mean': result.target_mean,
         'target_std': result.target_std,
         'metrics': {'name': name, 'config_name': cfg.name, 'seq_len': seq_len,

@@ -30,7 +30,7 @@ def synthetic_head(layer_idx: int, head_idx: int, seq_len: int, num_layers: int,
                    head_dim: int) -> tuple[torch.Tensor, torch.Tensor]:
     """Keys and values [seq_len, head_dim] fp32 of one (layer, head)."""
     rng = np.random.RandomState(layer_idx * num_kv_heads + head_idx)
-    t = torch.linspace(0, 1, seq_len).numpy()            # fp32 grid, promoted in the float64 math below
+    t = torch.linspace(0, 1, seq_len).numpy()            # fp32 grid: python_float * float32 array stays float32 (NumPy 2), as in the reference
     sharp = 1.0 + 2.0 * (layer_idx / max(num_layers - 1, 1))
     n_spikes = int(3 * sharp)
     max_width = max(2, int(5 / sharp))

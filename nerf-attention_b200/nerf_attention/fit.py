@@ -214,11 +214,18 @@ def _result_to_record(name: str, layer: int, head: int, kv_type: str, result: Fi
     return dict(zip(RECORD_KEYS, values))
 
 
+def detached_state(model: SIREN) -> dict[str, torch.Tensor]:
+    """state_dict with every tensor copied out of its storage.  After a batched fit the parameters are views into
+    one flat buffer holding ALL jobs' weights (batched.adopt_packed); torch.save serialises whole storages, so saving
+    the views would write every fit's weights into every checkpoint."""
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
 def _save_model(output_dir: Path, name: str, result: FitResult, record: dict) -> None:
     """Checkpoint dict consumed by evaluate._load_model_from_checkpoint (reference fit.py:121-137)."""
     cfg = result.config
     torch.save({
-        'model_state': result.model.state_dict(),
+        'model_state': detached_state(result.model),
         'config': {'hidden_features': cfg.hidden_features, 'hidden_layers': cfg.hidden_layers,
                    'omega_0': cfg.omega_0, 'name': cfg.name, 'out_features': result.d_head},
         'target_mean': result.target_mean,

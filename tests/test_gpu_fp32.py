@@ -214,3 +214,39 @@ def test_progress_metrics_match_reference_logging(cuda_device, capsys, precision
     quiet = na.fit_many([na.FitJob(kv, cfg, model_from_state(cfg, 128, state))], epochs=60, device='cuda',
                         verbose=False, precision=precision)[0]
     assert quiet.progress == [] and quiet.losses == res.losses
+
+
+def test_prenormalised_targets_give_the_same_fit(cuda_device):
+    """NA_FIT_TARGETS_PRENORMALISED: handing in (t - mean) / std with the statistics must train the same model and
+    report the same de-normalised metrics as handing in the raw tensor (siren.py:85-87 done by the caller)."""
+    cfg = na.SIRENConfig(64, 1, 30.0, 'kat')
+    kv = smooth_tensor(11, 200, 64) * 3.0 + 1.5
+    state = seeded_state(cfg, 64, 5)
+    mean, std, t_norm = orc.normalise(kv)
+    raw = gpu_fit(kv, cfg, 30, 'fp32', state)
+    job = na.FitJob(t_norm.contiguous(), cfg, model_from_state(cfg, 64, state), target_mean=mean, target_std=std)
+    pre = na.fit_many([job], epochs=30, device='cuda', verbose=False, precision='fp32')[0]
+    assert np.allclose(pre.losses, raw.losses, rtol=1e-5)
+    assert pre.final_mse == pytest.approx(raw.final_mse, rel=1e-4)
+    assert pre.final_cosine_mean == pytest.approx(raw.final_cosine_mean, abs=1e-6)
+    assert np.allclose(pre.cosine_sims, raw.cosine_sims, atol=1e-5)
+    assert torch.allclose(pre.target_mean, mean, atol=0) and torch.allclose(pre.target_std, std, atol=0)
+
+
+def test_per_position_cosine_matches_the_fit_records(cuda_device, tmp_path):
+    """evaluate.per_position_cosine (reference evaluate.py:148-153) from the saved checkpoints and layer files equals
+    the cosine_sims the fit itself reported, and the checkpoints are the reference's size."""
+    from nerf_attention.evaluate import per_position_cosine, plot_per_position_error
+    kv_dir, out_dir = tmp_path / 'kv', tmp_path / 'fits'
+    na.extract_kv_cache_synthetic(seq_len=192, num_layers=4, num_kv_heads=2, head_dim=64, output_dir=kv_dir)
+    records = na.fit_kv_cache(kv_dir, out_dir, epochs=25, device='cuda', quick=True, precision='fp32')
+    curves = per_position_cosine(out_dir, kv_dir, device='cuda')
+    assert len(curves) == 4 and all(c.shape == (192,) for c in curves.values())
+    by_name = {r['name']: r for r in records}
+    for name, curve in curves.items():
+        assert float(curve.mean()) == pytest.approx(by_name[name]['final_cosine_mean'], abs=2e-5)
+        assert float(curve.min()) == pytest.approx(by_name[name]['final_cosine_min'], abs=2e-5)
+        size = (out_dir / f'{name}_model.pt').stat().st_size
+        assert size <= 4 * by_name[name]['num_parameters'] + 16384          # its own weights only, not the batch buffer
+    plot_per_position_error(out_dir, kv_dir, tmp_path / 'figs', device='cuda')
+    assert (tmp_path / 'figs' / 'per_position_cosine.json').exists()

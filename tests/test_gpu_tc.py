@@ -115,8 +115,10 @@ def test_unsupported_shapes_fail_loudly(cuda_device):
     cfg = na.SIRENConfig(64, 1, 30.0, 'x')
     with pytest.raises(_native.NativeError, match='bf16 path needs'):
         gpu_fit(smooth_tensor(1, 128, 16), cfg, 1, 'bf16', seeded_state(cfg, 16, 1))
-    with pytest.raises(_native.NativeError, match='not implemented'):
+    with pytest.raises(ValueError, match='precision must be one of'):                 # only fp32 and bf16 exist
         gpu_fit(smooth_tensor(1, 128, 128), cfg, 1, 'tf32', seeded_state(cfg, 128, 1))
+    with pytest.raises(_native.NativeError, match='not implemented'):                 # precision code 1 is unassigned
+        gpu_fit(smooth_tensor(1, 128, 128), cfg, 1, 1, seeded_state(cfg, 128, 1))
 
 
 @pytest.mark.parametrize('mode,tol', [(0, 1.5e-7), (1, 6e-7)])

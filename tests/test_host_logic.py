@@ -212,7 +212,7 @@ def test_argument_validation_without_a_gpu():
     f = fits[0]
     f.N, f.D, f.H, f.L, f.omega0 = 2048, 128, 256, 2, 30.0
     f.positions = f.targets = f.params = 1 << 20                                            # never dereferenced
-    assert lib.nerfattn_fit_workspace_bytes(fits, 1, 1, ctypes.byref(need)) == -2          # TF32 reserved
+    assert lib.nerfattn_fit_workspace_bytes(fits, 1, 1, ctypes.byref(need)) == -2          # precision code 1 is unassigned
     assert b'precision' in lib.nerfattn_last_error()
     assert lib.nerfattn_fit_workspace_bytes(fits, 1, 0, ctypes.byref(need)) == 0
     fp32_bytes = need.value
@@ -274,3 +274,44 @@ def test_async_layer_loader_and_job_specs(tmp_path):
     assert specs[2]['name'] == 'L0_H0_value_small' and specs[-1]['name'] == 'L2_H1_value_medium'
     assert all(s['tensor'] is None for s in specs)
     assert torch.equal(jobs[2]['tensor'], blobs[0]['values'][0]) and torch.equal(jobs[-1]['tensor'], blobs[2]['values'][1])
+
+
+def test_checkpoint_holds_only_its_own_weights(tmp_path):
+    """After a batched fit every model's parameters are views into one flat buffer with all jobs' weights; a
+    checkpoint must still be ~4 * num_parameters bytes (the reference's size), not the whole buffer."""
+    from nerf_attention.types import FitResult
+    cfg = na.SIRENConfig(64, 1, 30.0, 'medium')
+    model = na.SIREN(cfg, out_features=16)
+    p = model.count_parameters()
+    big = torch.zeros(4_000_000)                               # stands in for FitBatch.params.buf (16 MB)
+    batched.pack_model(model, big[1000:1000 + p])
+    batched.adopt_packed(model, big[1000:1000 + p])
+    assert model.network[0].linear.weight.untyped_storage().nbytes() == big.numel() * 4     # really a view
+    result = FitResult(model=model, config=cfg, target_mean=torch.zeros(1, 16), target_std=torch.ones(1, 16), losses=[0.1],
+                       final_mse=0.0, final_cosine_mean=1.0, final_cosine_min=1.0, final_cosine_std=0.0,
+                       per_pos_mse=np.zeros(8, np.float32), cosine_sims=np.ones(8, np.float32), compression_ratio=1.0,
+                       raw_size_bytes=256, siren_size_bytes=4 * p, train_time_seconds=0.0, seq_len=8, d_head=16,
+                       num_parameters=p)
+    record = fit_mod._result_to_record('L0_H0_key_medium', 0, 0, 'key', result)
+    fit_mod._save_model(tmp_path, 'L0_H0_key_medium', result, record)
+    size = (tmp_path / 'L0_H0_key_medium_model.pt').stat().st_size
+    assert 4 * p <= size <= 4 * p + 16384, (size, 4 * p)
+    ckpt = torch.load(tmp_path / 'L0_H0_key_medium_model.pt', weights_only=True)
+    assert all(torch.equal(ckpt['model_state'][k], v) for k, v in model.state_dict().items())
+    from nerf_attention.experiments import scaling
+    scaling._save_scaling_checkpoint(tmp_path / 's.pt', 'L0_H0_K', result, 8)
+    assert (tmp_path / 's.pt').stat().st_size <= 4 * p + 16384
+
+
+def test_reference_export_names_exist_and_say_what_they_are():
+    """Every name the reference package exports (reference nerf_attention/__init__.py) imports; the figure functions and
+    the real-LLM extraction are outside the hot path and raise a clear error instead of an ImportError."""
+    reference_exports = ['CONFIGS_FULL', 'CONFIGS_QUICK', 'AnalysisResult', 'FitResult', 'KVMetadata', 'LayerSummary',
+                         'SIRENConfig', 'SIREN', 'SineLayer', 'fit_siren', 'extract_kv_cache', 'extract_kv_cache_synthetic',
+                         'analyze_kv_cache', 'fit_kv_cache', 'load_results', 'plot_pareto_frontier', 'plot_keys_vs_values',
+                         'plot_per_position_error', 'profile_latency', 'generate_summary_figure']
+    for name in reference_exports:
+        assert hasattr(na, name), name
+    for name in ('plot_pareto_frontier', 'plot_keys_vs_values', 'generate_summary_figure'):
+        with pytest.raises(NotImplementedError, match='outside the scope'):
+            getattr(na, name)([], Path('.'))
