@@ -343,7 +343,7 @@ def fp32_record(jobs, initial, args, dev, clocks_mhz) -> dict:
 def decode_record(dev, peaks) -> dict:
     """BASELINE's second metric (config 4 + the 32768-token end of the crossover table): fused SIREN-eval + q.k (bf16
     tensor path, K never materialised) vs a measured fp16 KV-read + q.k from HBM, `medium` architecture.  Heads per
-    launch are chosen so that the KV side streams >= 128 MB per launch (a 256-head launch at 512 tokens is 33 MB = 5 us
+    launch are chosen so that the KV side streams >= 256 MB per launch (a 256-head launch at 512 tokens is 33 MB = 5 us
     at HBM speed, which measures launch ramp, not bandwidth); both sides process the same heads per launch."""
     import nerf_attention as na
     from nerf_attention.evaluate import profile_decode
@@ -353,7 +353,7 @@ def decode_record(dev, peaks) -> dict:
     sampler = ClockSampler(dev.index or 0).start()
     rows = []
     for n in (512, 1024, 2048, 4096, 32768):
-        heads = int(min(1024, max(64, (128 << 20) // (n * HEAD_DIM * 2))))
+        heads = int(min(2048, max(64, (256 << 20) // (n * HEAD_DIM * 2))))
         r = profile_decode(models, [n], heads_per_launch=heads, precisions=('bf16',), device=str(dev), warmup=5, runs=30)[0]
         rows.append({'seq_len': n, 'heads_per_launch': heads, 'kv_bytes_per_launch': r['kv_bytes_per_launch'],
                      'kvread_us': r['kvread_us'], 'kvread_gbs': r['kvread_gbs'], 'kvread_frac_of_hbm_peak': r['kvread_gbs'] / peaks['hbm_gbs'],

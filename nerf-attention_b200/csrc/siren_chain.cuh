@@ -130,6 +130,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, uint64_t pol) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
                  ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
@@ -529,6 +539,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         // a reduction and one MUFU per element) instead of being parked in the scratch: a third of the scratch traffic
         // (and its DRAM spill) for the price of SFU work moved from the longest step into the shortest
         constexpr bool recompute_cos0 = !FWD && NA_RECOMPUTE_COS0;
+        // One slot and H <= 256: the accumulator needs 256 of the 512 TMEM columns; the other 256 park cos_l of the hidden
+        // layers (two bf16 per 32-bit cell, H / 2 columns per layer, the thread's own lane and columns) instead of the
+        // global scratch -- written with tcgen05.st in the sine epilogue, read back with tcgen05.ld next to the
+        // accumulator in the backward half: no L2 / DRAM round trip at all.  Layers that do not fit (deep: the third
+        // hidden layer at H = 256) keep using the scratch.
+        constexpr bool COSTM = !FWD && NS == 1 && H <= 256;
+        constexpr int COSTM_LAYERS = COSTM ? 256 / (H / 2) : 0;
+        const uint32_t t_cos0 = tmem_base + 256 + ((uint32_t)(q * 32) << 16) + col0 / 2;     // layer l at + (l - 1) * H / 2
         // cos scratch of one layer: [H/16 units][128 rows][16 columns], so that the 32 lanes of a warp (consecutive
         // rows, 32 B each) touch 1 KB of contiguous memory per access instead of 32 lines at row stride
         constexpr int SCR_U = BM * 16;                // elements between consecutive 16-column units
@@ -684,7 +702,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         if (!(FWD && s == L)) {
                             act_store16(act_u32, r, col0 + u * 16, so);
 #ifndef NA_EXP_NOSCRATCH
-                            if (!FWD) st_global_256_hint(cdst + u * SCR_U, co, pol_keep);
+                            if (COSTM && s <= COSTM_LAYERS) tmem_st8(t_cos0 + (s - 1) * (H / 2) + u * 8, co);
+                            else if (!FWD) st_global_256_hint(cdst + u * SCR_U, co, pol_keep);
 #endif
                         } else if (MODE == 2) {
                             // sum the 16 columns over the 32 rows of this warp: transpose-reduce, 16 shuffles
@@ -733,11 +752,14 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     auto out_unit = [&](int u, uint32_t (&tt)[16]) {
                         uint32_t v[16];
                         tmem_ld16(t_out + u * 16, v);
+                        float4 b4[4];                            // the unit's output bias: in flight together with the TMEM load
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bsrc + u * 16) + j);
                         tmem_ld_wait();
                         uint32_t dout[8];
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bsrc + u * 16 + j));
+                            const float4 bb = b4[j / 4];
                             const float e0 = rmask * ((__uint_as_float(v[j + 0]) + bb.x) - __uint_as_float(tt[j + 0]));
                             const float e1 = rmask * ((__uint_as_float(v[j + 1]) + bb.y) - __uint_as_float(tt[j + 1]));
                             const float e2 = rmask * ((__uint_as_float(v[j + 2]) + bb.z) - __uint_as_float(tt[j + 2]));
@@ -764,6 +786,12 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         const float x = __ldg(rec->pos + row_c);
                         const float* w0 = g.psc + (size_t)fit * g.psc_fit + col0;
                         const float* b0 = g.psc + (size_t)fit * g.psc_fit + H + col0;
+                        // weights / biases of the next 8 columns, requested one group ahead as in layer 0: with 228 KB of the
+                        // SM's array given to shared memory these 32-byte loads come from L2 (~300 cycles), and a load issued
+                        // right before its use stalled all four warps of a scheduler (4.5 % of the kernel's stall samples)
+                        float4 wn[2], bn[2];
+                        wn[0] = __ldg(reinterpret_cast<const float4*>(w0)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0) + 1);
+                        bn[0] = __ldg(reinterpret_cast<const float4*>(b0)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0) + 1);
                         NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
                         mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;
                         NA_T1();
@@ -775,15 +803,15 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                             float cs[16];
 #pragma unroll
                             for (int gi = 0; gi < 2; ++gi) {         // the same arguments and sin/cos routine as layer 0 (s == 0)
-                                const float4* wp = reinterpret_cast<const float4*>(w0 + u * 16 + gi * 8);
-                                const float4* bp = reinterpret_cast<const float4*>(b0 + u * 16 + gi * 8);
                                 float arg[8], sn[8], c8[8];
 #pragma unroll
                                 for (int j = 0; j < 2; ++j) {
-                                    const float4 wv = __ldg(wp + j), bv = __ldg(bp + j);
-                                    arg[4 * j] = fmaf(x, wv.x, bv.x); arg[4 * j + 1] = fmaf(x, wv.y, bv.y);
-                                    arg[4 * j + 2] = fmaf(x, wv.z, bv.z); arg[4 * j + 3] = fmaf(x, wv.w, bv.w);
+                                    arg[4 * j] = fmaf(x, wn[j].x, bn[j].x); arg[4 * j + 1] = fmaf(x, wn[j].y, bn[j].y);
+                                    arg[4 * j + 2] = fmaf(x, wn[j].z, bn[j].z); arg[4 * j + 3] = fmaf(x, wn[j].w, bn[j].w);
                                 }
+                                const int nxt = (u * 2 + gi + 1 < NU * 2) ? (u * 2 + gi + 1) * 8 : 0;
+                                wn[0] = __ldg(reinterpret_cast<const float4*>(w0 + nxt)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0 + nxt) + 1);
+                                bn[0] = __ldg(reinterpret_cast<const float4*>(b0 + nxt)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0 + nxt) + 1);
                                 if (mufu_l0) sincos8<true>(arg, sn, c8); else sincos8<false>(arg, sn, c8);
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) cs[gi * 8 + j] = c8[j];
@@ -795,6 +823,33 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                                 dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * cs[2 * t]),
                                                     __uint_as_float(v[2 * t + 1]) * (omega * cs[2 * t + 1]));
                             if (u + 1 < NU) tmem_ld16(t_row + (u + 1) * 16, v);
+                            act_store16(act_u32, r, col0 + u * 16, dout);
+                        }
+                    } else if (COSTM && lp <= COSTM_LAYERS) {
+                        const uint32_t t_c = t_cos0 + (lp - 1) * (H / 2);
+                        NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;
+                        NA_T1();
+                        tc_fence_after();
+                        uint32_t va[16], vb[16], ca[8], cb[8];
+                        tmem_ld16(t_row, va); tmem_ld8(t_c, ca);
+#pragma unroll
+                        for (int u = 0; u < NU; ++u) {
+                            uint32_t (&v)[16] = (u & 1) ? vb : va;
+                            uint32_t (&c)[8] = (u & 1) ? cb : ca;
+                            tmem_ld_wait();
+                            if (u + 1 < NU) {
+                                tmem_ld16(t_row + (u + 1) * 16, (u & 1) ? va : vb);
+                                tmem_ld8(t_c + (u + 1) * 8, (u & 1) ? ca : cb);
+                            }
+                            uint32_t dout[8];
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                float c0, c1;
+                                unpack_bf16(c[t], c0, c1);
+                                dout[t] = pack_bf16(__uint_as_float(v[2 * t]) * (omega * c0),
+                                                    __uint_as_float(v[2 * t + 1]) * (omega * c1));
+                            }
                             act_store16(act_u32, r, col0 + u * 16, dout);
                         }
                     } else {
@@ -836,6 +891,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 t_kind[s == 0 ? 0 : s <= L ? 1 : s == L + 1 ? 2 : 3] += (clock64() - ts) - (t_acc - t_acc0);
 #endif
                 if (FWD && s == nsteps - 1) { tc_fence_before(); continue; }     // nothing consumes the last forward step
+                if (COSTM && s >= 1 && s <= L && s <= COSTM_LAYERS) tmem_st_wait();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
                 tc_fence_before();
                 __syncwarp();

@@ -36,6 +36,9 @@ def label(name):
     m = re.search(r'chain_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+)', name)
     if m:
         return f'chain<H={m.group(1)}, slots={m.group(2)}, cluster={m.group(4)}>'
+    m = re.search(r'dw_adam_kernel<(?:\(int\))?(\d+)', name)
+    if m:
+        return f'dw_adam<BN={m.group(1)}>'
     m = re.search(r'tc_gemm_kernel<(?:\(na::tc::Mode\))?(\d)', name)
     if m:
         return 'tc_gemm[' + ['raw', 'fwd_sine', 'fwd_out', 'dx', 'dw', 'fwd_dot'][int(m.group(1))] + ']'
@@ -52,8 +55,10 @@ for k, r in seq[i0:]:
         break
     if 'mirror' in k or 'scale_params' in k:      # one-off plan set-up, not part of an epoch
         continue
+    if 'xop' in k:                                # one-off plan set-up
+        continue
     picked.append((k, r))
-    if 'adam' in k:
+    if 'adam_kernel' in k and 'dw_adam' not in k:
         adam += 1
         if adam == 5 * epochs:
             break
@@ -73,11 +78,14 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 print(f'{tot / epochs:10.1f} total per epoch (serialised, cold-cache ncu times)')
 
 chain = [a for k, a in agg.items() if k.startswith('chain')]
+dwa = [a for k, a in agg.items() if k.startswith('dw_adam')]
 out = {
     'source': f'{path}: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum '
               f'--clock-control none, NERFATTN_NO_GRAPH=1 python bench.py --steps 1 --warmup 0 --epochs 3 --no-e2e; '
               f'first {epochs} epochs',
     'chain_dram_bytes_per_epoch': int(sum(a[2] + a[3] for a in chain) / epochs),
+    'dw_adam_dram_bytes_per_epoch': int(sum(a[2] + a[3] for a in dwa) / epochs),
+    'dw_adam_us_per_epoch_ncu': round(sum(a[1] for a in dwa) / epochs, 1),
     'step_dram_bytes_per_epoch': int(sum(a[2] + a[3] for a in agg.values()) / epochs),
     'chain_us_per_epoch_ncu': round(sum(a[1] for a in chain) / epochs, 1),
     'step_us_per_epoch_ncu': round(tot / epochs, 1),
