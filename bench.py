@@ -432,7 +432,19 @@ def run_native(args) -> None:
     dev = torch.device('cuda', local_rank)
     if wsize > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', rank=rank, world_size=wsize, device_id=dev)
+        # NCCL announces its version on stdout when the first communicator is built; stdout carries exactly one JSON
+        # line, so the set-up and the first collective run with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', rank=rank, world_size=wsize, device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _native.lib()                                            # fail loudly before any timing
 
     def barrier():
@@ -503,7 +515,8 @@ def run_native(args) -> None:
     torch.cuda.empty_cache()
 
     # ---- the kernels of a step, one class at a time, live: the profiling build of the library (libnerfattn_prof.so)
-    # honours NERFATTN_PHASE (1 = chain kernels only, 2 = dW + Adam kernels only, 8 = neither; the 2H-parameter
+    # honours NERFATTN_PHASE (1 = chain kernels only, 2 = dW + Adam kernels only, 16 = the fit-resident kernels of the
+    # tiny / small fits only -- they run beside the others in a real step --, 8 = none; the 2H-parameter
     # layer-0 Adam launch that ends an epoch always runs), so the difference to the "neither" run is that class's
     # device time per epoch (CUDA events on this stream; results of such runs are meaningless and discarded).
     phases = None
@@ -531,13 +544,16 @@ def run_native(args) -> None:
         phases = {'epochs': pe, 'fixed_ms': base_ms,
                   'chain_ms_per_epoch': (phase_ms(1) - base_ms) / pe,
                   'dw_adam_ms_per_epoch': (phase_ms(2) - base_ms) / pe,
+                  'resident_ms_per_epoch': (phase_ms(16) - base_ms) / pe,
                   'all_ms_per_epoch': (phase_ms(7) - base_ms) / pe,
                   'note': 'fixed_ms = set-up + final evaluation + the layer-0 Adam launches of all epochs'}
         pbatch.collect()
         del pbatch
         torch.cuda.empty_cache()
-    cos_keys = float(np.mean([r.final_cosine_mean for s, r in zip(specs, results) if s[2] == 0]))
-    cos_vals = float(np.mean([r.final_cosine_mean for s, r in zip(specs, results) if s[2] == 1]))
+    # mean final CosSim of the whole sweep (all ranks): [is_value, cos] rows through the metrics all-gather
+    cos_rows = gather_rows(np.array([[s[2], r.final_cosine_mean] for s, r in zip(specs, results)], dtype=np.float64), dev)
+    cos_keys = float(cos_rows[cos_rows[:, 0] == 0, 1].mean())
+    cos_vals = float(cos_rows[cos_rows[:, 0] == 1, 1].mean())
 
     # ---- end-to-end arm: public API, host tensors in, results out, every step
     e2e = None

@@ -21,6 +21,7 @@
 #include "siren_tc.cuh"
 #include "siren_chain.cuh"
 #include "siren_dw.cuh"
+#include "siren_resident.cuh"
 #include "decode.cuh"
 #include "synth.cuh"
 
@@ -40,6 +41,9 @@ static bool env_flag(const char* name) {
     return v && v[0] && strcmp(v, "0") != 0;
 }
 static bool chain_enabled() { return !env_flag("NERFATTN_NO_CHAIN"); }
+// narrow one-hidden-layer fits (tiny, small) train in the fit-resident kernel (siren_resident.cuh); NERFATTN_NO_RESIDENT=1
+// sends them through the row-tile chain like every other shape (the tests compare the two)
+static bool resident_enabled() { return chain_enabled() && !env_flag("NERFATTN_NO_RESIDENT"); }
 
 // ------------------------------------------------------------------ planning
 struct Group {
@@ -65,6 +69,7 @@ struct Group {
     // fused row-tile chain (siren_chain.cuh): forward + loss + dX chain in one kernel; cosb[l] then
     // holds dz_l (the dW operand) and cos_l lives in the per-CTA scratch
     bool use_chain;
+    bool use_resident;     // siren_resident.cuh: one persistent CTA per fit, one launch for all epochs (no per-epoch kernels)
     __nv_bfloat16* chain_scratch;
     float* psc;            // omega-prescaled W0 / sine-layer biases [nf][(L+2)H]
     chain::ChainMaps cmaps;
@@ -110,7 +115,8 @@ static int validate(const na_fit_t* fits, int nfits, int precision) {
         if (f.L > kMaxHidden) { set_error("fit %d: hidden_layers %d > %d", i, f.L, kMaxHidden); return NA_ERR_UNSUPPORTED; }
         if (f.H % 8 || f.D % 4) { set_error("fit %d: H must be a multiple of 8 and D a multiple of 4", i); return NA_ERR_UNSUPPORTED; }
         if (precision == NA_PREC_BF16 && !tc::shape_supported(f.N, f.D, f.H, f.L) &&
-            !(chain_enabled() && chain::shape_supported(f.N, f.D, f.H, f.L))) {
+            !(chain_enabled() && chain::shape_supported(f.N, f.D, f.H, f.L)) &&
+            !(resident_enabled() && res::shape_supported(f.N, f.D, f.H, f.L))) {
             set_error("fit %d: bf16 path needs H in {64,128,256,512}, D in {64,128,256} and hidden_layers >= 1 "
                       "(any N), or N %% 128 == 0 without hidden layers (got N=%d D=%d H=%d L=%d)", i, f.N, f.D, f.H, f.L);
             return NA_ERR_UNSUPPORTED;
@@ -172,10 +178,17 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
         g.nf = (int)g.fit_idx.size();
         g.mtiles = ceil_div(g.N, 128);
         g.d_recs = ar.take<FitRec>(g.nf);
-        g.use_chain = bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
+        g.use_resident = bf && resident_enabled() && res::shape_supported(g.N, g.D, g.H, g.L);
+        g.use_chain = !g.use_resident && bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
         g.d_epoch = ar.take<int>(64);
         g.d_done = ar.take<unsigned int>(64);
         const size_t nh = (size_t)g.nf * g.N * g.H, nd = (size_t)g.nf * g.N * g.D;
+        if (g.use_resident) {                              // everything between two Adam steps lives on the fit's SM
+            g.yeval = ar.take<float>(nd);
+            g.evalact[0] = ar.take<float>(nh); g.evalact[1] = ar.take<float>(nh);
+            g.nsplit = 1; g.ksplit = g.N;
+            continue;
+        }
         for (int l = 0; l <= g.L; ++l) {
             g.act[l] = ar.take<char>(nh * esz);
             if (l > 0 || !g.use_chain) g.cosb[l] = ar.take<char>(nh * esz);          // chain: dz_0 never leaves the SM
@@ -426,10 +439,15 @@ static void reap_graphs() {
 struct CaptureKit {
     int device = -1;
     cudaStream_t cap = nullptr;
+    cudaStream_t aux = nullptr;                   // carries the fit-resident kernels beside the epoch graphs
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     std::vector<cudaStream_t> streams;            // lanes / per-group branches
     std::vector<cudaEvent_t> events;              // fork, joins, cross-lane dependencies
     bool grow(size_t nstreams, size_t nevents) {
         if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (!aux && cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (!aux_fork && cudaEventCreateWithFlags(&aux_fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (!aux_join && cudaEventCreateWithFlags(&aux_join, cudaEventDisableTiming) != cudaSuccess) return false;
         while (streams.size() < nstreams) {
             cudaStream_t st = nullptr;
             if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -506,10 +524,11 @@ extern "C" long long nerfattn_fit_launch_count(const na_fit_t* fits, int32_t nfi
     long long per_epoch = 0, fin = 0;
     for (const Group& g : plan.groups) {
         // layer0 + L fwd + out + (L+1) x (dW, dX) + Adam; the tensor path adds the layer-0 gradient kernel
-        if (g.use_chain) per_epoch += 3;                          // chain, dW + Adam, Adam of layer 0
+        if (g.use_resident) setup += 1;                           // one launch for all epochs
+        else if (g.use_chain) per_epoch += 3;                     // chain, dW + Adam, Adam of layer 0
         else per_epoch += 1 + g.L + 1 + 2 * (g.L + 1) + 1 + (precision == NA_PREC_BF16 ? 1 : 0);
         fin += 1 + g.L + 1 + 2;
-        if (precision == NA_PREC_BF16) setup += 1;   // bf16 weight mirror
+        if (precision == NA_PREC_BF16 && !g.use_resident) setup += 1;   // bf16 weight mirror
     }
     return setup + per_epoch * epochs + fin;
 }
@@ -577,7 +596,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             r.cos = f.cos_sims; r.ppmse = f.per_pos_mse; r.scalars = f.scalars;
             r.mean_out = f.mean; r.std_out = f.std; r.omega = f.omega0; r.uniq = u; r.fit_index = g.fit_idx[k];
             r.prenorm = (f.flags & NA_FIT_TARGETS_PRENORMALISED) ? 1 : 0;
-            r.posid = g.posid[k];
+            r.posid = g.posid.empty() ? 0 : g.posid[k];
         }
         NA_CUDA_OK(cudaMemcpyAsync(g.d_recs, recs.data(), g.nf * sizeof(FitRec), cudaMemcpyHostToDevice, stream));
     }
@@ -633,8 +652,10 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
         if ((rc = tc::configure_all())) return rc;
         if ((rc = chain::configure_all())) return rc;
         if ((rc = dw::configure_all())) return rc;
+        if ((rc = res::configure_all())) return rc;
         for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
             Group& g = plan.groups[gi];
+            if (g.use_resident) continue;
             if (g.use_chain) {
                 if ((rc = chain::build_maps(g.N, g.D, g.H, g.L, g.nf, g.lm, g.wbf16, g.act, g.cosb, g.dy, g.xop,
                                             g.mtiles * (int)g.pos_tabs.size(), g.cmaps))) return rc;
@@ -668,7 +689,27 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
         launch_adam(g, plan, beta1, beta2, eps, s);
         return NA_OK;
     };
-    const size_t ng = plan.groups.size();
+    // groups with per-epoch kernels (eg) and fit-resident groups (rg: one launch covers a whole stretch of epochs)
+    std::vector<const Group*> eg, rg;
+    for (const Group& g : plan.groups) (g.use_resident ? rg : eg).push_back(&g);
+    const size_t ng = eg.size();
+    auto launch_resident = [&](int e0, int count, cudaStream_t s) -> int {
+        if (!(chain::phase_mask() & 16)) return NA_OK;
+        for (const Group* gp : rg) {
+            const Group& g = *gp;
+            res::ResArgs a{};
+            a.N = g.N; a.mtiles = g.mtiles; a.recs = g.d_recs;
+            for (int l = 0; l < 3; ++l) { a.w_off[l] = g.lm.w_off[l]; a.b_off[l] = g.lm.b_off[l]; }
+            a.e_begin = e0; a.e_count = count;
+            a.step_size = plan.d_step_size; a.bc2 = plan.d_bc2;
+            a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
+            a.loss_scale = 2.0f / ((float)g.N * (float)g.D); a.loss_inv_count = 1.0f / ((float)g.N * (float)g.D);
+            a.sincos_mode = chain::sincos_mode();
+            int r2 = res::launch(g.H, g.D, a, g.nf, s);
+            if (r2) return r2;
+        }
+        return NA_OK;
+    };
     // Two-lane schedule of the chain path (all groups on it, at least two of them): the chain kernels of all groups run
     // back to back on the "compute lane" with grid_c persistent CTAs, each group's dW + Adam follows on the "memory
     // lane" with the remaining SMs while the next group's chain kernel runs -- the chain is FP32/SFU-issue-bound with
@@ -680,7 +721,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     // stages + the Adam stream in flight per SM), so its time grows as 148 / grid_m (0.54 -> 1.29 ms on 40 SMs) and
     // the memory lane becomes the bottleneck; the SM-time of the two halves is conserved.
     bool all_chain = precision == NA_PREC_BF16;
-    for (const Group& g : plan.groups) all_chain = all_chain && g.use_chain;
+    for (const Group* g : eg) all_chain = all_chain && g->use_chain;
     int grid_c = 0;
     { const char* e = getenv("NERFATTN_LANES"); if (e) grid_c = atoi(e); }
     grid_c &= ~1;                                           // CTA pairs
@@ -693,7 +734,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
         int r2 = NA_OK;
         if (!kit || ng == 1) {
             for (int e = 0; e < count && !r2; ++e)
-                for (size_t gi = 0; gi < ng && !r2; ++gi) r2 = group_epoch(plan.groups[gi], main);
+                for (size_t gi = 0; gi < ng && !r2; ++gi) r2 = group_epoch(*eg[gi], main);
         } else if (lanes) {
             cudaStream_t lc = kit->streams[0], lm = kit->streams[1];
             cudaEvent_t* ev = kit->events.data();            // [0] fork, [1] [2] joins, [3 + 2g] chain done, [4 + 2g] Adam done
@@ -702,7 +743,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             cudaStreamWaitEvent(lm, ev[0], 0);
             for (int e = 0; e < count && !r2; ++e)
                 for (size_t gi = 0; gi < ng && !r2; ++gi) {
-                    const Group& g = plan.groups[gi];
+                    const Group& g = *eg[gi];
                     if (e > 0) cudaStreamWaitEvent(lc, ev[4 + 2 * gi], 0);       // this group's previous epoch has ended
                     if ((r2 = chain_part(g, grid_c, lc))) break;
                     cudaEventRecord(ev[3 + 2 * gi], lc);
@@ -718,7 +759,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             for (size_t gi = 0; gi < ng; ++gi) {
                 cudaStream_t sg = kit->streams[gi];
                 cudaStreamWaitEvent(sg, ev[0], 0);
-                for (int e = 0; e < count && !r2; ++e) r2 = group_epoch(plan.groups[gi], sg);
+                for (int e = 0; e < count && !r2; ++e) r2 = group_epoch(*eg[gi], sg);
                 cudaEventRecord(ev[1 + gi], sg);
                 cudaStreamWaitEvent(main, ev[1 + gi], 0);
             }
@@ -742,13 +783,15 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     };
     const bool logging = log_every > 0 && progress;
 
+    // epochs until the next progress evaluation (or the end): the stretch a fit-resident launch covers
+    auto stretch = [&](int e) { return logging ? std::min(epochs - e, log_every - ((e + 1) % log_every)) : epochs - e; };
     if (epochs > 0) {
         if (!env_flag("NERFATTN_NO_GRAPH")) {
             // Graphs of up to `glen` epochs (NERFATTN_GRAPH_EPOCHS), replayed; a shorter one covers remainders and the
             // stretches between progress evaluations.  Replays are stream-ordered, so the lanes drain once per replay.
             int glen = 20;
             { const char* e = getenv("NERFATTN_GRAPH_EPOCHS"); if (e && atoi(e) > 0) glen = atoi(e); }
-            KitLease lease(lanes ? 2 : ng, lanes ? 3 + 2 * ng : 1 + ng);
+            KitLease lease(lanes ? 2 : std::max<size_t>(ng, 1), lanes ? 3 + 2 * ng : 1 + ng);
             if (!lease.kit) { set_error("cannot create capture streams / events: %s", cudaGetErrorString(cudaGetLastError())); return NA_ERR_CUDA; }
             std::map<int, GraphHold> graphs;                  // by length; destroyed on every early return
             auto graph_of = [&](int len, cudaGraphExec_t* out) -> int {
@@ -765,25 +808,42 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
                 *out = gh.exec;
                 return NA_OK;
             };
+            int res_until = 0;                               // the fit-resident launches cover epochs [0, res_until)
+            bool res_pending = false;
             for (int e = 0; e < epochs;) {
+                if (res_pending && e >= res_until) { NA_CUDA_OK(cudaStreamWaitEvent(stream, lease.kit->aux_join, 0)); res_pending = false; }
                 if ((rc = log_progress(e))) return rc;
-                int len = std::min(glen, epochs - e);
-                if (logging) len = std::min(len, log_every - ((e + 1) % log_every));   // stop before the next evaluation point
-                len = std::max(len, 1);
+                if (!rg.empty() && e >= res_until) {
+                    // the fit-resident groups run this whole stretch in one launch per group, beside the epoch graphs of the
+                    // other groups (their CTAs take an SM each for the stretch; the graphs' persistent kernels get the rest)
+                    const int len = stretch(e);
+                    cudaStream_t rs = ng ? lease.kit->aux : stream;
+                    if (ng) { NA_CUDA_OK(cudaEventRecord(lease.kit->aux_fork, stream)); NA_CUDA_OK(cudaStreamWaitEvent(rs, lease.kit->aux_fork, 0)); }
+                    if ((rc = launch_resident(e, len, rs))) return rc;
+                    if (ng) { NA_CUDA_OK(cudaEventRecord(lease.kit->aux_join, rs)); res_pending = true; }
+                    res_until = e + len;
+                }
+                if (!ng) { e = res_until; continue; }
+                int len = std::max(1, std::min(glen, stretch(e)));
                 cudaGraphExec_t exec = nullptr;
                 if ((rc = graph_of(len, &exec))) return rc;
                 cudaError_t ce = cudaGraphLaunch(exec, stream);
                 if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
                 e += len;
             }
+            if (res_pending) NA_CUDA_OK(cudaStreamWaitEvent(stream, lease.kit->aux_join, 0));
             for (auto& kv : graphs) {                        // still running: destroyed by a later call
                 if (kv.second.exec) park_graph(kv.second.exec, kv.second.graph, stream);
                 kv.second.release();
             }
         } else {
-            for (int e = 0; e < epochs; ++e) {
+            for (int e = 0; e < epochs;) {
                 if ((rc = log_progress(e))) return rc;
-                if ((rc = record_epochs(1, stream, nullptr))) return rc;
+                const int len = stretch(e);
+                if ((rc = launch_resident(e, len, stream))) return rc;
+                for (int k = 0; k < len; ++k)
+                    if (ng && (rc = record_epochs(1, stream, nullptr))) return rc;
+                e += len;
             }
         }
     }

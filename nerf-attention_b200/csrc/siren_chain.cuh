@@ -1042,17 +1042,17 @@ inline int sincos_mode() {
 // Profiling switches exist only in libnerfattn_prof.so (-DNA_PROFILING, `make libnerfattn_prof.so`); the release
 // library always launches every kernel and has no debug addressing.
 // NERFATTN_PHASE (results are meaningless): 1 = launch only the chain kernels of an epoch, 2 = only the dW GEMMs
-// (+ their fused Adam), 4 = only the stand-alone Adam kernels; 8 = none; 0 / unset = everything.  bench.py loads the
+// (+ their fused Adam), 16 = only the fit-resident kernels; 8 = none; 0 / 7 / unset = everything.  bench.py loads the
 // profiling build beside the release one to time the dominant kernel alone, live, with CUDA events.
 #ifdef NA_PROFILING
-inline int phase_mask() {
+inline int phase_mask() {                          // + 16 = the fit-resident kernels (siren_resident.cuh); 7 / unset = everything
     const char* e = getenv("NERFATTN_PHASE");
     const int m = e ? atoi(e) : 0;
-    return m ? m : 7;
+    return (m && m != 7) ? m : 23;
 }
 inline int chain_dbg() { const char* e = getenv("NERFATTN_CHAIN_DBG"); return e ? atoi(e) : 0; }
 #else
-constexpr int phase_mask() { return 7; }
+constexpr int phase_mask() { return 23; }
 constexpr int chain_dbg() { return 0; }
 #endif
 

@@ -184,3 +184,50 @@ def test_chain_kernel_agrees_with_unfused_path(cuda_device, monkeypatch, h, l, w
     # bitwise run-to-run determinism of the fused path
     a, b = run(20), run(20)
     assert a.losses == b.losses and torch.equal(flat(a.model.state_dict()), flat(b.model.state_dict()))
+
+
+@pytest.mark.parametrize('h,w,n,d', [(64, 30.0, 256, 128), (128, 30.0, 384, 128), (64, 60.0, 200, 64), (128, 15.0, 1000, 128)])
+def test_resident_kernel_agrees_with_chain_path(cuda_device, monkeypatch, h, w, n, d):
+    """The fit-resident kernel (siren_resident.cuh: one persistent CTA per fit, all epochs in one launch) and the row-tile
+    chain + grouped dW / Adam kernels are two implementations of the same bf16 training step for narrow one-hidden-layer
+    SIRENs: one-step gradients and a short trajectory must agree to bf16 rounding, ragged lengths included."""
+    cfg = na.SIRENConfig(h, 1, w, 'kat')
+    state = seeded_state(cfg, d, 123)
+    kv = smooth_tensor(9, n, d)
+
+    def run(epochs, resident):
+        monkeypatch.delenv('NERFATTN_NO_RESIDENT', raising=False)
+        if not resident:
+            monkeypatch.setenv('NERFATTN_NO_RESIDENT', '1')
+        return gpu_fit(kv, cfg, epochs, 'bf16', state, keep_optimizer_state=True)
+
+    ref1, got1 = run(1, False), run(1, True)
+    assert got1.losses[0] == pytest.approx(ref1.losses[0], rel=1e-4)
+    g_ref, g = ref1.model.adam_state[0].cpu(), got1.model.adam_state[0].cpu()
+    assert torch.nn.functional.cosine_similarity(g, g_ref, dim=0).item() > 0.99999
+    assert g.norm().item() == pytest.approx(g_ref.norm().item(), rel=1e-3)
+    ref, got = run(80, False), run(80, True)
+    assert np.allclose(got.losses, ref.losses, rtol=2e-3)
+    assert abs(got.final_cosine_mean - ref.final_cosine_mean) <= 5e-4
+    # against the oracle, and deterministic
+    orc_fit = oracle_fit(kv, cfg, 80, state)
+    assert abs(got.final_cosine_mean - orc_fit.final_cosine_mean) <= COS_ATOL_BF16
+    again = run(80, True)
+    assert again.losses == got.losses and torch.equal(flat(again.model.state_dict()), flat(got.model.state_dict()))
+
+
+def test_resident_groups_beside_epoch_graphs_and_progress(cuda_device):
+    """A mixed sweep: tiny / small fits train in the fit-resident kernel on a side stream while the other architectures
+    replay their epoch graphs; progress evaluations (siren.py:107-115) split both into the same stretches."""
+    from nerf_attention.extract import synthetic_head
+    keys, values = synthetic_head(3, 1, 256, 32, 8, 128)
+    spec = [(t, c, seeded_state(c, 128, 70 + i)) for t in (keys, values) for i, c in enumerate(na.CONFIGS_FULL)]
+    jobs = [na.FitJob(t, c, model_from_state(c, 128, s)) for t, c, s in spec]
+    res = na.fit_many(jobs, epochs=90, device='cuda', verbose=False, precision='bf16', log_every=40, progress=True)
+    ref = na.fit_many([na.FitJob(t, c, model_from_state(c, 128, s)) for t, c, s in spec], epochs=90, device='cuda',
+                      verbose=False, precision='fp32', log_every=40, progress=True)
+    for x, y in zip(res, ref):
+        assert abs(x.final_cosine_mean - y.final_cosine_mean) <= COS_ATOL_BF16, x.config.name
+        assert [p[0] for p in x.progress] == [40, 80] and len(x.losses) == 90
+        for (e, nm, rm, cs), (_, nm2, rm2, cs2) in zip(x.progress, y.progress):
+            assert nm == pytest.approx(nm2, rel=3e-2) and cs == pytest.approx(cs2, abs=COS_ATOL_BF16)
