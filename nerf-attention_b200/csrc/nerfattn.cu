@@ -439,15 +439,21 @@ static void reap_graphs() {
 struct CaptureKit {
     int device = -1;
     cudaStream_t cap = nullptr;
-    cudaStream_t aux = nullptr;                   // carries the fit-resident kernels beside the epoch graphs
-    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    std::vector<cudaStream_t> aux;                // one per fit-resident group: their kernels run beside the epoch graphs
+    std::vector<cudaEvent_t> aux_join;
+    cudaEvent_t aux_fork = nullptr;
     std::vector<cudaStream_t> streams;            // lanes / per-group branches
     std::vector<cudaEvent_t> events;              // fork, joins, cross-lane dependencies
-    bool grow(size_t nstreams, size_t nevents) {
+    bool grow(size_t nstreams, size_t nevents, size_t naux) {
         if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) return false;
-        if (!aux && cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) return false;
         if (!aux_fork && cudaEventCreateWithFlags(&aux_fork, cudaEventDisableTiming) != cudaSuccess) return false;
-        if (!aux_join && cudaEventCreateWithFlags(&aux_join, cudaEventDisableTiming) != cudaSuccess) return false;
+        while (aux.size() < naux) {
+            cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return false;
+            aux.push_back(st);
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+            aux_join.push_back(ev);
+        }
         while (streams.size() < nstreams) {
             cudaStream_t st = nullptr;
             if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -465,7 +471,7 @@ static std::mutex g_kit_mu;
 static std::vector<CaptureKit*> g_kits;          // idle kits of every device
 struct KitLease {
     CaptureKit* kit = nullptr;
-    KitLease(size_t nstreams, size_t nevents) {
+    KitLease(size_t nstreams, size_t nevents, size_t naux) {
         const int dev = tc::current_device();
         {
             std::lock_guard<std::mutex> lk(g_kit_mu);
@@ -473,7 +479,7 @@ struct KitLease {
                 if (g_kits[i]->device == dev) { kit = g_kits[i]; g_kits[i] = g_kits.back(); g_kits.pop_back(); break; }
         }
         if (!kit) { kit = new CaptureKit(); kit->device = dev; }
-        if (!kit->grow(nstreams, nevents)) {                  // leave what exists in the pool; the caller reports the CUDA error
+        if (!kit->grow(nstreams, nevents, naux)) {                  // leave what exists in the pool; the caller reports the CUDA error
             std::lock_guard<std::mutex> lk(g_kit_mu);
             g_kits.push_back(kit);
             kit = nullptr;
@@ -677,11 +683,13 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
 
     // ---- epoch loop
     // One epoch of one group, all of it on stream s (eager mode, fp32, unfused tensor path, single-group calls).
-    auto group_epoch = [&](const Group& g, cudaStream_t s) -> int {
+    // cap: most CTAs a persistent kernel of this epoch may use (0 = all SMs) -- while fit-resident kernels hold an SM
+    // each, a 148-CTA persistent grid would run as two or three ragged waves on what is left
+    auto group_epoch = [&](const Group& g, cudaStream_t s, int cap) -> int {
         if (precision == NA_PREC_FP32) { fp32_epoch(g, plan, beta1, beta2, eps, s); return NA_OK; }
         if (g.use_chain) {
-            int r2 = chain_part(g, 0, s);
-            return r2 ? r2 : update_part(g, plan, beta1, beta2, eps, 0, s);
+            int r2 = chain_part(g, cap, s);
+            return r2 ? r2 : update_part(g, plan, beta1, beta2, eps, cap, s);
         }
         int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy, g.gradpart,
                            g.colpart, g.colpart_layer_off, g.xpart, g.losspart, g.losspart_per_fit, g.mtiles, s);
@@ -693,10 +701,13 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     std::vector<const Group*> eg, rg;
     for (const Group& g : plan.groups) (g.use_resident ? rg : eg).push_back(&g);
     const size_t ng = eg.size();
-    auto launch_resident = [&](int e0, int count, cudaStream_t s) -> int {
+    // `streams`: one per fit-resident group (their kernels use an SM per fit, so different groups run side by side), or
+    // null: all on `s`
+    auto launch_resident = [&](int e0, int count, cudaStream_t s, const cudaStream_t* streams) -> int {
         if (!(chain::phase_mask() & 16)) return NA_OK;
-        for (const Group* gp : rg) {
-            const Group& g = *gp;
+        for (size_t ri = 0; ri < rg.size(); ++ri) {
+            const Group& g = *rg[ri];
+            if (streams) s = streams[ri];
             res::ResArgs a{};
             a.N = g.N; a.mtiles = g.mtiles; a.recs = g.d_recs;
             for (int l = 0; l < 3; ++l) { a.w_off[l] = g.lm.w_off[l]; a.b_off[l] = g.lm.b_off[l]; }
@@ -730,11 +741,11 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     const int grid_m = sms - grid_c;
 
     // Enqueue `count` epochs of every group behind whatever is on `main`; with a kit (stream capture) the groups fan out.
-    auto record_epochs = [&](int count, cudaStream_t main, CaptureKit* kit) -> int {
+    auto record_epochs = [&](int count, cudaStream_t main, CaptureKit* kit, int cap) -> int {
         int r2 = NA_OK;
         if (!kit || ng == 1) {
             for (int e = 0; e < count && !r2; ++e)
-                for (size_t gi = 0; gi < ng && !r2; ++gi) r2 = group_epoch(*eg[gi], main);
+                for (size_t gi = 0; gi < ng && !r2; ++gi) r2 = group_epoch(*eg[gi], main, cap);
         } else if (lanes) {
             cudaStream_t lc = kit->streams[0], lm = kit->streams[1];
             cudaEvent_t* ev = kit->events.data();            // [0] fork, [1] [2] joins, [3 + 2g] chain done, [4 + 2g] Adam done
@@ -759,7 +770,7 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             for (size_t gi = 0; gi < ng; ++gi) {
                 cudaStream_t sg = kit->streams[gi];
                 cudaStreamWaitEvent(sg, ev[0], 0);
-                for (int e = 0; e < count && !r2; ++e) r2 = group_epoch(*eg[gi], sg);
+                for (int e = 0; e < count && !r2; ++e) r2 = group_epoch(*eg[gi], sg, cap);
                 cudaEventRecord(ev[1 + gi], sg);
                 cudaStreamWaitEvent(main, ev[1 + gi], 0);
             }
@@ -791,14 +802,14 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             // stretches between progress evaluations.  Replays are stream-ordered, so the lanes drain once per replay.
             int glen = 20;
             { const char* e = getenv("NERFATTN_GRAPH_EPOCHS"); if (e && atoi(e) > 0) glen = atoi(e); }
-            KitLease lease(lanes ? 2 : std::max<size_t>(ng, 1), lanes ? 3 + 2 * ng : 1 + ng);
+            KitLease lease(lanes ? 2 : std::max<size_t>(ng, 1), lanes ? 3 + 2 * ng : 1 + ng, rg.size());
             if (!lease.kit) { set_error("cannot create capture streams / events: %s", cudaGetErrorString(cudaGetLastError())); return NA_ERR_CUDA; }
-            std::map<int, GraphHold> graphs;                  // by length; destroyed on every early return
-            auto graph_of = [&](int len, cudaGraphExec_t* out) -> int {
-                GraphHold& gh = graphs[len];
+            std::map<std::pair<int, int>, GraphHold> graphs;  // by (length, CTA cap); destroyed on every early return
+            auto graph_of = [&](int len, int cap, cudaGraphExec_t* out) -> int {
+                GraphHold& gh = graphs[std::make_pair(len, cap)];
                 if (!gh.exec) {
                     NA_CUDA_OK(cudaStreamBeginCapture(lease.kit->cap, cudaStreamCaptureModeThreadLocal));
-                    const int r2 = record_epochs(len, lease.kit->cap, lease.kit);
+                    const int r2 = record_epochs(len, lease.kit->cap, lease.kit, cap);
                     cudaError_t ce = cudaStreamEndCapture(lease.kit->cap, &gh.graph);   // always ends the capture, also after an error
                     if (r2) return r2;
                     if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
@@ -810,28 +821,36 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             };
             int res_until = 0;                               // the fit-resident launches cover epochs [0, res_until)
             bool res_pending = false;
+            // (Replaying the first epochs from graphs whose persistent grids are capped to the SMs the fit-resident CTAs leave
+            // free was measured: no difference, 175.4-176.0 k fit-epochs/s for caps over 0-60 epochs -- CTAs that find
+            // their SM taken simply start when one frees up.)
             for (int e = 0; e < epochs;) {
-                if (res_pending && e >= res_until) { NA_CUDA_OK(cudaStreamWaitEvent(stream, lease.kit->aux_join, 0)); res_pending = false; }
+                if (res_pending && e >= res_until) {
+                    for (size_t ri = 0; ri < rg.size(); ++ri) NA_CUDA_OK(cudaStreamWaitEvent(stream, lease.kit->aux_join[ri], 0));
+                    res_pending = false;
+                }
                 if ((rc = log_progress(e))) return rc;
                 if (!rg.empty() && e >= res_until) {
                     // the fit-resident groups run this whole stretch in one launch per group, beside the epoch graphs of the
                     // other groups (their CTAs take an SM each for the stretch; the graphs' persistent kernels get the rest)
                     const int len = stretch(e);
-                    cudaStream_t rs = ng ? lease.kit->aux : stream;
-                    if (ng) { NA_CUDA_OK(cudaEventRecord(lease.kit->aux_fork, stream)); NA_CUDA_OK(cudaStreamWaitEvent(rs, lease.kit->aux_fork, 0)); }
-                    if ((rc = launch_resident(e, len, rs))) return rc;
-                    if (ng) { NA_CUDA_OK(cudaEventRecord(lease.kit->aux_join, rs)); res_pending = true; }
+                    NA_CUDA_OK(cudaEventRecord(lease.kit->aux_fork, stream));
+                    for (size_t ri = 0; ri < rg.size(); ++ri) NA_CUDA_OK(cudaStreamWaitEvent(lease.kit->aux[ri], lease.kit->aux_fork, 0));
+                    if ((rc = launch_resident(e, len, stream, lease.kit->aux.data()))) return rc;
+                    for (size_t ri = 0; ri < rg.size(); ++ri) NA_CUDA_OK(cudaEventRecord(lease.kit->aux_join[ri], lease.kit->aux[ri]));
+                    res_pending = true;
                     res_until = e + len;
                 }
                 if (!ng) { e = res_until; continue; }
                 int len = std::max(1, std::min(glen, stretch(e)));
                 cudaGraphExec_t exec = nullptr;
-                if ((rc = graph_of(len, &exec))) return rc;
+                if ((rc = graph_of(len, 0, &exec))) return rc;
                 cudaError_t ce = cudaGraphLaunch(exec, stream);
                 if (ce != cudaSuccess) { set_error("graph launch failed: %s", cudaGetErrorString(ce)); return NA_ERR_CUDA; }
                 e += len;
             }
-            if (res_pending) NA_CUDA_OK(cudaStreamWaitEvent(stream, lease.kit->aux_join, 0));
+            if (res_pending)
+                for (size_t ri = 0; ri < rg.size(); ++ri) NA_CUDA_OK(cudaStreamWaitEvent(stream, lease.kit->aux_join[ri], 0));
             for (auto& kv : graphs) {                        // still running: destroyed by a later call
                 if (kv.second.exec) park_graph(kv.second.exec, kv.second.graph, stream);
                 kv.second.release();
@@ -840,9 +859,9 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
             for (int e = 0; e < epochs;) {
                 if ((rc = log_progress(e))) return rc;
                 const int len = stretch(e);
-                if ((rc = launch_resident(e, len, stream))) return rc;
+                if ((rc = launch_resident(e, len, stream, nullptr))) return rc;
                 for (int k = 0; k < len; ++k)
-                    if (ng && (rc = record_epochs(1, stream, nullptr))) return rc;
+                    if (ng && (rc = record_epochs(1, stream, nullptr, 0))) return rc;
                 e += len;
             }
         }

@@ -95,6 +95,21 @@ __device__ __forceinline__ void load16(uint32_t base, uint32_t chunk_bytes, int 
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[4]), "=r"(pk[5]), "=r"(pk[6]), "=r"(pk[7])
                  : "r"(rowaddr + (uint32_t)(((u0 + 1) ^ (r & 7)) << 4)) : "memory");
 }
+// Adam for the fit-resident kernel: the same update as f32::adam_update with the two IEEE divisions and the IEEE square
+// root replaced by the SFU approximations (sqrt.approx, rcp.approx: <= 2 ulp each) and 1 / bc2 folded into a multiply.
+// The exact sequences are ~100 issue slots per parameter and were 19 % of this kernel's stall samples; the deviation
+// (~1e-7 relative per step) is three orders of magnitude below the bf16 rounding of the gradient itself, and the fp32
+// parity mode never runs this kernel.
+__device__ __forceinline__ void adam_fast(float g, float& m, float& v, float& w, float ob1, float beta2, float ob2,
+                                          float eps, float inv_bc2, float nss) {
+    m = fmaf(ob1, g - m, m);
+    v = fmaf(v, beta2, (ob2 * g) * g);
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    float rc;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(sq, inv_bc2, eps)));
+    w = fmaf(nss * m, rc, w);
+}
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 template <int H, int D>
@@ -161,6 +176,15 @@ resident_kernel(const ResArgs g) {
             const uint32_t i_bh = make_idesc(H, false, true);                                         // backward: MN-major B
             const uint32_t i_dw = make_idesc(H, true, true), i_one = make_idesc(16, true, false), i_x = make_idesc(XOP_N, true, false);
             auto wait_ready = [&] { mbar_wait(act_ready, rdy); rdy ^= 1u; tc_fence_after(); };
+            // descriptors: the start-address field (bytes >> 4) is the only part that changes inside a step
+            auto kmaj = [](uint32_t base) { return make_desc(base, 0, 1024); };                       // K-major, chunk-advanced by hand
+            const uint64_t a_h0 = kmaj(s_h0), a_h1 = kmaj(s_h1), a_dy = kmaj(s_dy), a_c1 = kmaj(s_c1);
+            const uint64_t b_w1 = kmaj(s_w1), b_wf = kmaj(s_wf), b_one = kmaj(s_ones), b_x = kmaj(s_xop);
+            const uint64_t bt_wf = make_desc(s_wf, D * 128, 1024), bt_w1 = make_desc(s_w1, H * 128, 1024);   // MN-major weights (backward)
+            const uint64_t t_dy = make_desc(s_dy, CHUNK, 1024), t_h1 = make_desc(s_h1, CHUNK, 1024);       // MN-major activations (dW)
+            const uint64_t t_c1 = make_desc(s_c1, CHUNK, 1024), t_h0 = make_desc(s_h0, CHUNK, 1024);
+            auto koff = [](int k, int chunk_bytes) { return (uint64_t)(((k >> 2) * chunk_bytes + (k & 3) * 32) >> 4); };   // K-major: 16 columns = 32 B
+            constexpr uint64_t ROWS16 = (UMMA_K * 128) >> 4;                                               // MN-major: 16 rows of 128 B
             for (int e = 0; e < g.e_count; ++e) {
                 for (int t = 0; t < mtiles; ++t) {
                     const uint32_t accum = t > 0 ? 1u : 0u;             // gradient accumulators: fresh at the first tile of an epoch
@@ -169,8 +193,7 @@ resident_kernel(const ResArgs g) {
                     if (lane == 0) {
 #pragma unroll
                         for (int k = 0; k < H / UMMA_K; ++k)
-                            tc_mma_bf16(tmem_base + C::T_ACC, make_desc(s_h0 + (k >> 2) * CHUNK + (k & 3) * 32, 0, 1024),
-                                        make_desc(s_w1 + (k >> 2) * (H * 128) + (k & 3) * 32, 0, 1024), i_fh, k > 0 ? 1u : 0u);
+                            tc_mma_bf16(tmem_base + C::T_ACC, a_h0 + koff(k, CHUNK), b_w1 + koff(k, H * 128), i_fh, k > 0 ? 1u : 0u);
                         tc_commit(acc_full);
                     }
                     __syncwarp();
@@ -179,40 +202,38 @@ resident_kernel(const ResArgs g) {
                     if (lane == 0) {
 #pragma unroll
                         for (int k = 0; k < H / UMMA_K; ++k)
-                            tc_mma_bf16(tmem_base + C::T_ACC, make_desc(s_h1 + (k >> 2) * CHUNK + (k & 3) * 32, 0, 1024),
-                                        make_desc(s_wf + (k >> 2) * (D * 128) + (k & 3) * 32, 0, 1024), i_fd, k > 0 ? 1u : 0u);
+                            tc_mma_bf16(tmem_base + C::T_ACC, a_h1 + koff(k, CHUNK), b_wf + koff(k, D * 128), i_fd, k > 0 ? 1u : 0u);
                         tc_commit(acc_full);
                     }
                     __syncwarp();
-                    // step 3: dh1 = dY Wf;  dWf += dY^T h1;  dbf += dY^T 1
+                    // step 3: dh1 = dY Wf -- committed at once: the epilogue turns it into dz1 (in place over cos1, which no
+                    // MMA of this step reads) while dWf += dY^T h1 and dbf += dY^T 1 run behind it; the tensor pipe is in
+                    // order, so they are complete before anything of step 4 starts
                     wait_ready();
                     if (lane == 0) {
 #pragma unroll
                         for (int k = 0; k < D / UMMA_K; ++k)
-                            tc_mma_bf16(tmem_base + C::T_ACC, make_desc(s_dy + (k >> 2) * CHUNK + (k & 3) * 32, 0, 1024),
-                                        make_desc(s_wf + k * (UMMA_K * 128), D * 128, 1024), i_bh, k > 0 ? 1u : 0u);
+                            tc_mma_bf16(tmem_base + C::T_ACC, a_dy + koff(k, CHUNK), bt_wf + k * ROWS16, i_bh, k > 0 ? 1u : 0u);
+                        tc_commit(acc_full);
 #pragma unroll
                         for (int k = 0; k < BM / UMMA_K; ++k) {
-                            const uint64_t a = make_desc(s_dy + k * (UMMA_K * 128), CHUNK, 1024);
-                            tc_mma_bf16(tmem_base + C::T_DWF, a, make_desc(s_h1 + k * (UMMA_K * 128), CHUNK, 1024), i_dw, (accum | (uint32_t)(k > 0)));
-                            tc_mma_bf16(tmem_base + C::T_DBF, a, make_desc(s_ones + (k & 3) * 32, 0, 1024), i_one, (accum | (uint32_t)(k > 0)));
+                            tc_mma_bf16(tmem_base + C::T_DWF, t_dy + k * ROWS16, t_h1 + k * ROWS16, i_dw, (accum | (uint32_t)(k > 0)));
+                            tc_mma_bf16(tmem_base + C::T_DBF, t_dy + k * ROWS16, b_one + (uint64_t)((k & 3) * 2), i_one, (accum | (uint32_t)(k > 0)));
                         }
-                        tc_commit(acc_full);
                     }
                     __syncwarp();
-                    // step 4: dh0 = dz1 W1;  dW1 += dz1^T h0;  db1 += dz1^T 1
+                    // step 4: dW1 += dz1^T h0, db1 += dz1^T 1, dh0 = dz1 W1: one commit for all three -- the epilogue
+                    // overwrites h0 with dz0, so it may only start once dW1 has read h0
                     wait_ready();
                     if (lane == 0) {
 #pragma unroll
-                        for (int k = 0; k < H / UMMA_K; ++k)
-                            tc_mma_bf16(tmem_base + C::T_ACC, make_desc(s_c1 + (k >> 2) * CHUNK + (k & 3) * 32, 0, 1024),
-                                        make_desc(s_w1 + k * (UMMA_K * 128), H * 128, 1024), i_bh, k > 0 ? 1u : 0u);
-#pragma unroll
                         for (int k = 0; k < BM / UMMA_K; ++k) {
-                            const uint64_t a = make_desc(s_c1 + k * (UMMA_K * 128), CHUNK, 1024);
-                            tc_mma_bf16(tmem_base + C::T_DW1, a, make_desc(s_h0 + k * (UMMA_K * 128), CHUNK, 1024), i_dw, (accum | (uint32_t)(k > 0)));
-                            tc_mma_bf16(tmem_base + C::T_DB1, a, make_desc(s_ones + (k & 3) * 32, 0, 1024), i_one, (accum | (uint32_t)(k > 0)));
+                            tc_mma_bf16(tmem_base + C::T_DW1, t_c1 + k * ROWS16, t_h0 + k * ROWS16, i_dw, (accum | (uint32_t)(k > 0)));
+                            tc_mma_bf16(tmem_base + C::T_DB1, t_c1 + k * ROWS16, b_one + (uint64_t)((k & 3) * 2), i_one, (accum | (uint32_t)(k > 0)));
                         }
+#pragma unroll
+                        for (int k = 0; k < H / UMMA_K; ++k)
+                            tc_mma_bf16(tmem_base + C::T_ACC, a_c1 + koff(k, CHUNK), bt_w1 + k * ROWS16, i_bh, k > 0 ? 1u : 0u);
                         tc_commit(acc_full);
                     }
                     __syncwarp();
@@ -221,8 +242,7 @@ resident_kernel(const ResArgs g) {
                     if (lane == 0) {
 #pragma unroll
                         for (int k = 0; k < BM / UMMA_K; ++k)
-                            tc_mma_bf16(tmem_base + C::T_L0, make_desc(s_h0 + k * (UMMA_K * 128), CHUNK, 1024),
-                                        make_desc(s_xop + (k >> 2) * (XOP_BYTES / 2) + (k & 3) * 32, 0, 1024), i_x, (accum | (uint32_t)(k > 0)));
+                            tc_mma_bf16(tmem_base + C::T_L0, t_h0 + k * ROWS16, b_x + koff(k, XOP_BYTES / 2), i_x, (accum | (uint32_t)(k > 0)));
                         tc_commit(acc_full);
                     }
                     __syncwarp();
@@ -270,13 +290,21 @@ resident_kernel(const ResArgs g) {
                 const bool row_ok = row < g.N;
                 const int row_c = row_ok ? row : g.N - 1;
                 const float x = __ldg(rec.pos + row_c);
-                // targets of this thread (OW fp32): requested now, used three steps later
-                uint32_t tg[OW];
+                // targets of this thread (OW fp32): pulled into L2 now, loaded right before the OUT step waits for its MMA
                 const float* tn = rec.tnorm + (size_t)row_c * D + ocol0;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tn));
+                // ---------------- E0: layer 0 (fp32, siren.py:33-34 with in_features = 1).  The math runs while the previous
+                // tile's layer-0 gradient MMA still reads dz0 out of this buffer; only the stores wait for it.
+                uint32_t so0[NU][8];
 #pragma unroll
-                for (int j = 0; j < OW; j += 8) chain::ld_global_nc_na_256(tn + j, &tg[j]);
-                // ---------------- E0: layer 0 (fp32, siren.py:33-34 with in_features = 1); the buffer is free once the
-                // previous tile's layer-0 gradient MMA has read dz0
+                for (int u = 0; u < NU; ++u) {
+                    float arg[16], sn[16], cs[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) arg[j] = fmaf(x, w0s[col0 + u * 16 + j], b0s[col0 + u * 16 + j]);
+                    sincos16(arg, sn, cs, mufu_l0);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) so0[u][j / 2] = pack_bf16(sn[j], sn[j + 1]);
+                }
                 if (t > 0) wait_acc();
                 if (cg == 0) {                                       // the tile's positions as the B operand {1, x_hi, x_mid, x_lo}
                     const float xv = row_ok ? x : 0.f;
@@ -293,16 +321,7 @@ resident_kernel(const ResArgs g) {
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    float arg[16], sn[16], cs[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) arg[j] = fmaf(x, w0s[col0 + u * 16 + j], b0s[col0 + u * 16 + j]);
-                    sincos16(arg, sn, cs, mufu_l0);
-                    uint32_t so[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) so[j / 2] = pack_bf16(sn[j], sn[j + 1]);
-                    store16(s_h0, CHUNK, r, col0 + u * 16, so);
-                }
+                for (int u = 0; u < NU; ++u) store16(s_h0, CHUNK, r, col0 + u * 16, so0[u]);
                 hand_over();
                 // ---------------- S1: h1 = sin(w z1 + w b1), cos1 parked in shared memory
                 wait_acc();
@@ -323,6 +342,9 @@ resident_kernel(const ResArgs g) {
                 }
                 hand_over();
                 // ---------------- OUT: dY = 2 (y - t) / (N D), loss (siren.py:101)
+                uint32_t tg[OW];
+#pragma unroll
+                for (int j = 0; j < OW; j += 8) chain::ld_global_nc_na_256(tn + j, &tg[j]);
                 wait_acc();
                 {
                     const float rmask = row_ok ? 1.f : 0.f;
@@ -343,13 +365,16 @@ resident_kernel(const ResArgs g) {
                     }
                 }
                 hand_over();
-                // ---------------- DXF: dz1 = (dY Wf) * w cos1, in place over cos1
+                // ---------------- DXF: dz1 = (dY Wf) * w cos1, in place over cos1 (read while the MMA runs)
+                uint32_t cc1[NU][8];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) load16(s_c1, CHUNK, r, col0 + u * 16, cc1[u]);
                 wait_acc();
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
-                    uint32_t v[16], cc[8], dout[8];
+                    uint32_t v[16], dout[8];
+                    uint32_t (&cc)[8] = cc1[u];
                     tmem_ld16(t_lane + C::T_ACC + col0 + u * 16, v);
-                    load16(s_c1, CHUNK, r, col0 + u * 16, cc);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -360,20 +385,26 @@ resident_kernel(const ResArgs g) {
                     store16(s_c1, CHUNK, r, col0 + u * 16, dout);
                 }
                 hand_over();
-                // ---------------- DX1: dz0 = (dz1 W1) * w cos0, cos0 recomputed as in E0; over h0 (dW1 has read it)
-                wait_acc();
+                // ---------------- DX1: dz0 = (dz1 W1) * w cos0, cos0 recomputed as in E0 (while the MMAs run); over h0 (dW1 has read it)
+                float wc0[NU][16];
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
                     float arg[16], sn[16], cs[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) arg[j] = fmaf(x, w0s[col0 + u * 16 + j], b0s[col0 + u * 16 + j]);
                     sincos16(arg, sn, cs, mufu_l0);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) wc0[u][j] = omega * cs[j];
+                }
+                wait_acc();
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
                     uint32_t v[16], dout[8];
                     tmem_ld16(t_lane + C::T_ACC + col0 + u * 16, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        dout[j] = pack_bf16(__uint_as_float(v[2 * j]) * (omega * cs[2 * j]), __uint_as_float(v[2 * j + 1]) * (omega * cs[2 * j + 1]));
+                        dout[j] = pack_bf16(__uint_as_float(v[2 * j]) * wc0[u][2 * j], __uint_as_float(v[2 * j + 1]) * wc0[u][2 * j + 1]);
                     store16(s_h0, CHUNK, r, col0 + u * 16, dout);
                 }
                 hand_over();
@@ -381,7 +412,7 @@ resident_kernel(const ResArgs g) {
             wait_acc();                                              // the last tile's layer-0 gradient MMA: every accumulator is complete
 
             // ---------------- Adam (torch _single_tensor_adam order) straight from the TMEM accumulators
-            const float bc2 = g.bc2[ee], nss = -g.step_size[ee];
+            const float bc2 = 1.0f / g.bc2[ee], nss = -g.step_size[ee];      // bc2: the reciprocal (adam_fast)
             const float ob1 = 1.0f - g.beta1, ob2 = 1.0f - g.beta2;
             float* pw = rec.params; float* pm = rec.m; float* pv = rec.v;
             // weights of a [rows x H] layer: this thread owns row r, columns [col0, col0 + CW)
@@ -394,18 +425,23 @@ resident_kernel(const ResArgs g) {
                     tmem_ld_wait();
                     const size_t o = (size_t)w_off + (size_t)r * H + col0 + u * 16;
                     uint32_t nb[8];
+                    float4 w4[4], m4[4], v4[4];                      // 12 loads in flight before the first store (no aliasing stalls)
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 w4 = *reinterpret_cast<const float4*>(pw + o + j), m4 = *reinterpret_cast<const float4*>(pm + o + j);
-                        float4 v4 = *reinterpret_cast<const float4*>(pv + o + j);
-                        f32::adam_update(__uint_as_float(v[j]), m4.x, v4.x, w4.x, ob1, g.beta2, ob2, g.eps, bc2, nss);
-                        f32::adam_update(__uint_as_float(v[j + 1]), m4.y, v4.y, w4.y, ob1, g.beta2, ob2, g.eps, bc2, nss);
-                        f32::adam_update(__uint_as_float(v[j + 2]), m4.z, v4.z, w4.z, ob1, g.beta2, ob2, g.eps, bc2, nss);
-                        f32::adam_update(__uint_as_float(v[j + 3]), m4.w, v4.w, w4.w, ob1, g.beta2, ob2, g.eps, bc2, nss);
-                        *reinterpret_cast<float4*>(pm + o + j) = m4;
-                        *reinterpret_cast<float4*>(pv + o + j) = v4;
-                        *reinterpret_cast<float4*>(pw + o + j) = w4;
-                        nb[j / 2] = pack_bf16(w4.x, w4.y); nb[j / 2 + 1] = pack_bf16(w4.z, w4.w);
+                    for (int j = 0; j < 4; ++j) {
+                        w4[j] = *reinterpret_cast<const float4*>(pw + o + 4 * j);
+                        m4[j] = *reinterpret_cast<const float4*>(pm + o + 4 * j);
+                        v4[j] = *reinterpret_cast<const float4*>(pv + o + 4 * j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        adam_fast(__uint_as_float(v[4 * j]), m4[j].x, v4[j].x, w4[j].x, ob1, g.beta2, ob2, g.eps, bc2, nss);
+                        adam_fast(__uint_as_float(v[4 * j + 1]), m4[j].y, v4[j].y, w4[j].y, ob1, g.beta2, ob2, g.eps, bc2, nss);
+                        adam_fast(__uint_as_float(v[4 * j + 2]), m4[j].z, v4[j].z, w4[j].z, ob1, g.beta2, ob2, g.eps, bc2, nss);
+                        adam_fast(__uint_as_float(v[4 * j + 3]), m4[j].w, v4[j].w, w4[j].w, ob1, g.beta2, ob2, g.eps, bc2, nss);
+                        *reinterpret_cast<float4*>(pm + o + 4 * j) = m4[j];
+                        *reinterpret_cast<float4*>(pv + o + 4 * j) = v4[j];
+                        *reinterpret_cast<float4*>(pw + o + 4 * j) = w4[j];
+                        nb[2 * j] = pack_bf16(w4[j].x, w4[j].y); nb[2 * j + 1] = pack_bf16(w4[j].z, w4[j].w);
                     }
                     store16(s_w, (uint32_t)(rows * 128), r, col0 + u * 16, nb);
                 }
@@ -415,7 +451,7 @@ resident_kernel(const ResArgs g) {
             // vectors: one parameter per lane (TMEM lane = feature), spread over the column groups
             auto adam_one = [&](float gr, size_t pi) {
                 float mm = pm[pi], vv = pv[pi], ww = pw[pi];
-                f32::adam_update(gr, mm, vv, ww, ob1, g.beta2, ob2, g.eps, bc2, nss);
+                adam_fast(gr, mm, vv, ww, ob1, g.beta2, ob2, g.eps, bc2, nss);
                 pm[pi] = mm; pv[pi] = vv; pw[pi] = ww;
                 return ww;
             };

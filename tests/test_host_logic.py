@@ -315,3 +315,25 @@ def test_reference_export_names_exist_and_say_what_they_are():
     for name in ('plot_pareto_frontier', 'plot_keys_vs_values', 'generate_summary_figure'):
         with pytest.raises(NotImplementedError, match='outside the scope'):
             getattr(na, name)([], Path('.'))
+
+
+def test_bench_strong_scaling_shards_partition_the_one_sweep():
+    """bench.py --gpus N shards ONE 280-fit sweep (BASELINE config 3) by (layer, head, key|value) unit: every fit exactly
+    once over the ranks, 280 / N per rank, units kept whole; --scaling weak gives every rank a whole sweep."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', ROOT / 'bench.py')
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    full = bench.sweep_specs(0, 1, 'strong', 2048)
+    assert len(full) == 280 and full[0] == (0, 0, 0, 0) and full[-1] == (31, 3, 1, 6)
+    for world in (2, 4, 8):
+        shards = [bench.sweep_specs(r, world, 'strong', 2048) for r in range(world)]
+        assert sorted(s for sh in shards for s in sh) == sorted(full)
+        assert all(len(sh) == 280 // world for sh in shards)
+        for sh in shards:                                         # a unit's 7 architectures stay on one rank
+            units = {}
+            for layer, head, is_value, ci in sh:
+                units.setdefault((layer, head, is_value), []).append(ci)
+            assert all(sorted(v) == list(range(7)) for v in units.values())
+        weak = bench.sweep_specs(1, world, 'weak', 2048)
+        assert len(weak) == 280 and weak[0][0] == 1
