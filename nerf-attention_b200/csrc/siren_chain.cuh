@@ -48,7 +48,13 @@ constexpr int NEPI = 16;                          // epilogue warps 4..19
 constexpr int NTHREADS = (NCTRL + NEPI) * 32;     // 640
 constexpr int CHUNK_BYTES = BM * 64 * 2;          // one K-chunk of an A operand: 128 rows x 64 bf16
 constexpr int STAGE_BYTES = 256 * 64 * 2;         // one K-chunk of a weight operand: <= 256 x 64 bf16
-constexpr int SMEM_BUDGET = 227 * 1024 - 512;     // dynamic shared memory per CTA, minus the barrier block
+constexpr int BAR_BYTES = 512;                    // mbarriers (<= 32) + the TMEM base slot
+// What a tile needs from its FitRec, resolved once per round by one lane of every epilogue warp and kept in shared memory
+// (one record per warp and slot): held in registers across the step loop these values were spilled to local memory, and
+// with 228 KB of the SM's array given to shared memory the reloads came from L2 (profiles/README.md, round 2).
+struct alignas(16) SlotRec { int fit, mt; float omega; int pad0; const float* pos; const float* tnorm; const float* obias; const float* pad1; };
+constexpr int TAIL_BYTES = BAR_BYTES + 16 * 2 * (int)sizeof(SlotRec);
+constexpr int SMEM_BUDGET = 227 * 1024 - TAIL_BYTES;   // dynamic shared memory per CTA for the operand buffers and the weight ring
 
 // NS = tiles in flight per CTA (2 needs 2 x max(H, 256) accumulator columns and operand buffers)
 template <int H, int NS> struct Cfg {
@@ -64,7 +70,7 @@ template <int H, int NS> struct Cfg {
     static constexpr int ACT_BYTES = ACT_CHUNKS * CHUNK_BYTES;
     static constexpr int ACC_COLS = (H > 256) ? 512 : 256;
     static constexpr int STAGES = ((SMEM_BUDGET - NSLOT * ACT_BYTES) / STAGE_BYTES < 6) ? (SMEM_BUDGET - NSLOT * ACT_BYTES) / STAGE_BYTES : 6;
-    static constexpr int SMEM = NSLOT * ACT_BYTES + STAGES * STAGE_BYTES + 256;
+    static constexpr int SMEM = NSLOT * ACT_BYTES + STAGES * STAGE_BYTES + TAIL_BYTES;   // + barriers and the per-warp slot records
     static_assert(STAGES >= 3, "weight ring");
     static_assert(NU >= 1 && CW % 16 == 0, "column split");
 };
@@ -229,6 +235,9 @@ __device__ __forceinline__ Step step_info(int s, int L, int D) {
 
 #ifndef NA_RECOMPUTE_COS0
 #define NA_RECOMPUTE_COS0 1
+#endif
+#ifdef NA_EXP_TIMING                              // profiles/: per-step cycle counters of two epilogue warps, printed per launch
+#define NA_CHAIN_TIMING 1
 #endif
 template <bool MUFU>
 __device__ __forceinline__ void sincos8(const float (&x)[8], float (&s)[8], float (&c)[8]) {
@@ -550,7 +559,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         // cos scratch of one layer: [H/16 units][128 rows][16 columns], so that the 32 lanes of a warp (consecutive
         // rows, 32 B each) touch 1 KB of contiguous memory per access instead of 32 lines at row stride
         constexpr int SCR_U = BM * 16;                // elements between consecutive 16-column units
-        uint32_t acc_phase = 0, free_phase = 0;       // bit `slot` = parity of acc_full[slot] / buf_free[slot]
+        // Parity of the next wait on acc_full[slot] (and, training, on buf_free[slot]: always waited for in the same places):
+        // a slot waits once per step with an MMA behind it, so the parity follows from the round and the step -- no
+        // per-slot phase registers to carry (and spill) through the loop
+        auto wait_parity = [&](int round_, int s_) -> uint32_t {
+            return FWD ? (uint32_t)(round_ * (nsteps - 1) + s_ - 1) & 1u : (uint32_t)(round_ * nsteps + s_ - 1) & 1u;
+        };
+        SlotRec* const wrec = reinterpret_cast<SlotRec*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES) + ei * 2;
         // Layer-0 gradient partials of the tile a slot has just finished: the MMA warp left sum_r dz0[r][j] {1, x_hi, x_mid,
         // x_lo}[r] in 16 accumulator columns per 128 columns of dz_0 (lane = column j); the column group cg drains the
         // cg-th block.  Per-tile partials, summed over the row tiles in a fixed order by adam_kernel: deterministic.
@@ -582,19 +597,27 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
             const int tile0 = tile_of(round, 0), tile1 = (NSLOT > 1) ? tile_of(round, 1) : total_tiles;
             if (tile0 >= total_tiles) break;
             const bool two = tile1 < total_tiles;
-            const int fit0 = tile0 / g.mtiles, mt0 = tile0 - fit0 * g.mtiles;
-            const int fit1 = two ? tile1 / g.mtiles : fit0, mt1 = two ? tile1 - fit1 * g.mtiles : mt0;
-            const float omega0 = g.recs[fit0].omega, omega1 = g.recs[fit1].omega;
+            __syncwarp();                                      // every lane is done with the previous round's records
+            if (lane < NSLOT && (lane == 0 || two)) {
+                const int tile = lane ? tile1 : tile0;
+                SlotRec sr;
+                sr.fit = tile / g.mtiles; sr.mt = tile - sr.fit * g.mtiles;
+                const FitRec& fr = g.recs[sr.fit];
+                sr.omega = fr.omega; sr.pad0 = 0;
+                sr.pos = fr.pos; sr.tnorm = fr.tnorm; sr.obias = fr.params + g.b_off[L + 1]; sr.pad1 = nullptr;
+                wrec[lane] = sr;
+            }
+            __syncwarp();
             for (int s = 0; s < nsteps; ++s) {
 #pragma unroll 1
             for (int slot = 0; slot < NSLOT; ++slot) {
                 if (slot == 1 && !two) break;
-                const int fit = slot ? fit1 : fit0, mt = slot ? mt1 : mt0;
-                const FitRec* rec = &g.recs[fit];
+                const SlotRec* const rec = &wrec[slot];
+                const int fit = rec->fit, mt = rec->mt;
                 const int row = mt * BM + r;
                 const bool row_ok = row < g.N;                 // ragged last tile
                 const int row_c = row_ok ? row : g.N - 1;      // a valid row to read inputs from
-                const float omega = slot ? omega1 : omega0;
+                const float omega = rec->omega;
                 const uint32_t act_u32 = smem_u32(smem + slot * C::ACT_BYTES);
                 const uint32_t t_row = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + col0;
                 __nv_bfloat16* const scr = g.scratch + ((size_t)(blockIdx.x * NSLOT + slot) * (L + 1)) * (BM * H)
@@ -606,8 +629,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     // the buffer is free once the MMA warp has stored the previous tile's dz_0
                     if (!FWD && round > 0) {
                         NA_T0();
-                        mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;       // the layer-0 gradient MMA of the previous tile is complete
-                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;     // the store warp has seen the last step
+                        const uint32_t par = wait_parity(round, s); mbar_wait(&acc_full[slot], par);       // the layer-0 gradient MMA of the previous tile is complete
+                        mbar_wait(&buf_free[slot], par);     // the store warp has seen the last step
                         NA_T1();
                         tc_fence_after();
                         const int ptile = tile_of(round - 1, slot), pfit = ptile / g.mtiles;
@@ -651,8 +674,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     float4 bn[4];                                // bias of the next 16 columns (L1-resident)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) bn[j] = __ldg(reinterpret_cast<const float4*>(bsrc) + j);
-                    NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
-                    if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
+                    NA_T0(); const uint32_t par = wait_parity(round, s); mbar_wait(&acc_full[slot], par);
+                    if (!FWD) { mbar_wait(&buf_free[slot], par); }
                     NA_T1();
                     tc_fence_after();
                     __nv_bfloat16* const cdst = scr + (size_t)s * (BM * H);
@@ -736,15 +759,15 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                     // ---------------- output layer: dY = 2 (y - t) / (N D), loss partial (siren.py:101)
                     const int ow = D / C::CG;                    // output columns of this thread
                     const int ocol0 = cg * ow;
-                    const float* bsrc = rec->params + g.b_off[L + 1] + ocol0;
+                    const float* bsrc = rec->obias + ocol0;
                     const float* tn = rec->tnorm + (size_t)row_c * D + ocol0;
                     const float rmask = row_ok ? 1.f : 0.f;      // rows past the sequence: no loss, dY = 0, no gradient
                     const int nuo = ow / 16;
                     uint32_t ta[16], tb[16];                     // targets of this unit and the next: two units in flight
                     ld_global_nc_na_256(tn, &ta[0]); ld_global_nc_na_256(tn + 8, &ta[8]);
                     if (nuo > 1) { ld_global_nc_na_256(tn + 16, &tb[0]); ld_global_nc_na_256(tn + 24, &tb[8]); }
-                    NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
-                    if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
+                    NA_T0(); const uint32_t par = wait_parity(round, s); mbar_wait(&acc_full[slot], par);
+                    if (!FWD) { mbar_wait(&buf_free[slot], par); }
                     NA_T1();
                     tc_fence_after();
                     const uint32_t t_out = tmem_base + slot * C::ACC_COLS + ((uint32_t)(q * 32) << 16) + ocol0;
@@ -792,8 +815,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         float4 wn[2], bn[2];
                         wn[0] = __ldg(reinterpret_cast<const float4*>(w0)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0) + 1);
                         bn[0] = __ldg(reinterpret_cast<const float4*>(b0)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0) + 1);
-                        NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
-                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;
+                        NA_T0(); const uint32_t par = wait_parity(round, s); mbar_wait(&acc_full[slot], par);
+                        mbar_wait(&buf_free[slot], par);
                         NA_T1();
                         tc_fence_after();
                         uint32_t v[16];
@@ -827,8 +850,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         }
                     } else if (COSTM && lp <= COSTM_LAYERS) {
                         const uint32_t t_c = t_cos0 + (lp - 1) * (H / 2);
-                        NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
-                        mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot;
+                        NA_T0(); const uint32_t par = wait_parity(round, s); mbar_wait(&acc_full[slot], par);
+                        mbar_wait(&buf_free[slot], par);
                         NA_T1();
                         tc_fence_after();
                         uint32_t va[16], vb[16], ca[8], cb[8];
@@ -862,8 +885,8 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
 #endif
 #pragma unroll
                     for (int p = 0; p < PFD; ++p) NA_LD_COS(cc[p], csrc + p * SCR_U);
-                    NA_T0(); mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
-                    if (!FWD) { mbar_wait(&buf_free[slot], (free_phase >> slot) & 1u); free_phase ^= 1u << slot; }
+                    NA_T0(); const uint32_t par = wait_parity(round, s); mbar_wait(&acc_full[slot], par);
+                    if (!FWD) { mbar_wait(&buf_free[slot], par); }
                     NA_T1();
                     tc_fence_after();
                     uint32_t va[16], vb[16];
@@ -909,7 +932,7 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 const int ptile = (round > 0) ? tile_of(round - 1, slot) : total_tiles;
                 if (ptile >= total_tiles) continue;
                 const int pfit = ptile / g.mtiles;
-                mbar_wait(&acc_full[slot], (acc_phase >> slot) & 1u); acc_phase ^= 1u << slot;
+                mbar_wait(&acc_full[slot], wait_parity(round, 0));        // as the next tile's layer 0 would have waited
                 tc_fence_after();
                 drain_l0grad(slot, pfit, ptile - pfit * g.mtiles);
             }

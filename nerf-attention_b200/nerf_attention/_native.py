@@ -121,7 +121,7 @@ def prof_lib() -> ctypes.CDLL:
     calls this, and results of a phase-masked run are meaningless."""
     global _prof_lib
     if _prof_lib is None:
-        _prof_lib = _load(_PROF_LIB_PATH)
+        _prof_lib = _load(Path(os.environ.get('NERFATTN_PROF_LIB', _PROF_LIB_PATH)))   # experiment builds (profiles/)
     return _prof_lib
 
 

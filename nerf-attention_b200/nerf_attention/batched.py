@@ -14,6 +14,7 @@ Host/device traffic of one call (counted in ``TransferStats``):
 from __future__ import annotations
 
 import ctypes
+import functools
 import time
 from dataclasses import dataclass, field
 
@@ -54,7 +55,14 @@ last_stats = TransferStats()
 def lr_schedule(epochs: int, lr: float) -> np.ndarray:
     """lr seen by optimizer.step() at each epoch: Adam(lr) + CosineAnnealingLR(T_max=epochs,
     eta_min=0.01*lr), stepped after the optimizer (reference siren.py:90-93,103-104).  The
-    real torch scheduler runs on a dummy parameter so the float64 recursion is torch's own."""
+    real torch scheduler runs on a dummy parameter so the float64 recursion is torch's own.
+    Stepping it takes ~60 ms for 2000 epochs (most of a batched call's host set-up), so the
+    table is computed once per (epochs, lr); callers get a read-only array."""
+    return _lr_schedule_cached(int(epochs), float(lr))
+
+
+@functools.lru_cache(maxsize=32)
+def _lr_schedule_cached(epochs: int, lr: float) -> np.ndarray:
     dummy = torch.nn.Parameter(torch.zeros(1))
     opt = torch.optim.Adam([dummy], lr=lr)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=epochs, eta_min=lr * 0.01)
@@ -63,6 +71,7 @@ def lr_schedule(epochs: int, lr: float) -> np.ndarray:
         table[e] = opt.param_groups[0]['lr']
         opt.step()
         sched.step()
+    table.setflags(write=False)
     return table
 
 
