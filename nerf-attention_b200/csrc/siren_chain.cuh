@@ -85,6 +85,7 @@ struct ChainArgs {
     const float* pvec; float* pvpart;       // forward-only (decode, values): p [nf][N] fp32, partial sums [nf][N/32][H]
     const float* psc; int psc_fit;          // per fit w*W0[H], w*b0[H], w*b_1[H] .. w*b_L[H] (scale_params_kernel; Adam keeps it current)
     float* xpart; float* colpart0;          // training: layer-0 gradient partials per row tile [nf][mtiles][H]: sum_r dz0[r][j] x[r], sum_r dz0[r][j]
+    int pair_tiles;                         // tile_of(): adjacent tiles in the two slots of a CTA (set by launch_h)
     int dbg;                                // NERFATTN_CHAIN_DBG (libnerfattn_prof.so only; 0 in the release library)
     int sincos_mode;                        // bit 0: hidden layers, bit 1: layer 0 use the MUFU-core sincos (common.cuh)
 };
@@ -265,7 +266,13 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
     // tile of (round, slot): clusters stride over tile pairs, CTAs of a cluster take consecutive tiles
     const int cl_stride = (int)gridDim.x / CL;
-    auto tile_of = [&](int round, int slot) { return CL * ((int)blockIdx.x / CL + (round * NSLOT + slot) * cl_stride) + (int)crank; };
+    // g.pair_tiles (two slots, enough tiles to fill both everywhere): the two slots of a CTA take ADJACENT tiles, i.e. the
+    // same fit -- its layer-0 parameters, biases and weight prefetches are then shared by both slots through L1 / L2
+    // (-1.6 % kernel time); otherwise tiles are dealt round-robin so that a small launch spreads over all SMs first
+    auto tile_of = [&](int round, int slot) {
+        return (CL == 1 && NSLOT == 2 && g.pair_tiles) ? 2 * ((int)blockIdx.x + round * (int)gridDim.x) + slot
+                                                       : CL * ((int)blockIdx.x / CL + (round * NSLOT + slot) * cl_stride) + (int)crank;
+    };
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_ring = smem + NSLOT * C::ACT_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + STAGES * STAGE_SZ);
@@ -626,6 +633,16 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                 ts = clock64(); t_acc0 = t_acc;
 #endif
                 if (s == 0) {
+                    // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
+                    // The position and the first omega-prescaled weights / biases (kept current by Adam: one FFMA per argument)
+                    // are requested before the waits below: they come from L2 and would otherwise stall all four warps of a
+                    // scheduler at the top of every tile
+                    const float x = __ldg(rec->pos + row_c);
+                    const float* w0 = g.psc + (size_t)fit * g.psc_fit + col0;
+                    const float* b0 = g.psc + (size_t)fit * g.psc_fit + H + col0;
+                    float4 wn[2], bn[2];                         // weights / biases of the next 8 columns
+                    wn[0] = __ldg(reinterpret_cast<const float4*>(w0)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0) + 1);
+                    bn[0] = __ldg(reinterpret_cast<const float4*>(b0)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0) + 1);
                     // the buffer is free once the MMA warp has stored the previous tile's dz_0
                     if (!FWD && round > 0) {
                         NA_T0();
@@ -636,14 +653,6 @@ chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
                         const int ptile = tile_of(round - 1, slot), pfit = ptile / g.mtiles;
                         drain_l0grad(slot, pfit, ptile - pfit * g.mtiles);
                     }
-                    // ---------------- layer 0: outer product + sine, fp32 (siren.py:33-34 with in_features = 1)
-                    const float x = __ldg(rec->pos + row_c);
-                    // omega-prescaled layer-0 weights / biases (kept current by Adam): one FFMA per argument
-                    const float* w0 = g.psc + (size_t)fit * g.psc_fit + col0;
-                    const float* b0 = g.psc + (size_t)fit * g.psc_fit + H + col0;
-                    float4 wn[2], bn[2];                         // weights / biases of the next 8 columns
-                    wn[0] = __ldg(reinterpret_cast<const float4*>(w0)); wn[1] = __ldg(reinterpret_cast<const float4*>(w0) + 1);
-                    bn[0] = __ldg(reinterpret_cast<const float4*>(b0)); bn[1] = __ldg(reinterpret_cast<const float4*>(b0) + 1);
 #pragma unroll 1
                     for (int u = 0; u < NU; ++u) {
                         uint32_t so[8], co[8];
@@ -1031,11 +1040,13 @@ inline cudaError_t launch_mode(int mode, int grid, const ChainMaps& maps, const 
 }
 // mode: 0 training, 1 decode logits, 2 decode values.  The 2-CTA cluster variant exists for training only.
 template <int H>
-inline int launch_h(const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s, int max_ctas = 0) {
+inline int launch_h(const ChainMaps& maps, const ChainArgs& a_in, int mode, cudaStream_t s, int max_ctas = 0) {
+    ChainArgs a = a_in;
     const int tiles = a.nf * a.mtiles;
     const bool cl = mode == 0 && use_cluster(a.N, H, a.D);
     int grid = std::min(tiles, (max_ctas > 0) ? std::min(max_ctas, num_sms()) : num_sms());
     if (cl) grid &= ~1;
+    a.pair_tiles = (tiles >= 2 * grid && !getenv("NERFATTN_NO_PAIR_TILES")) ? 1 : 0;
     cudaError_t e;
     constexpr int NSD = (H <= 256) ? 2 : 1;                  // default slots
     if (cl && slots_for(H) == NSD) e = launch_one<H, NSD, 0, 2>(grid, maps, a, s);
