@@ -44,6 +44,27 @@ static bool chain_enabled() { return !env_flag("NERFATTN_NO_CHAIN"); }
 // narrow one-hidden-layer fits (tiny, small) train in the fit-resident kernel (siren_resident.cuh); NERFATTN_NO_RESIDENT=1
 // sends them through the row-tile chain like every other shape (the tests compare the two)
 static bool resident_enabled() { return chain_enabled() && !env_flag("NERFATTN_NO_RESIDENT"); }
+// widest hidden layer that takes the fit-resident kernel (NERFATTN_RESIDENT_MAX_H: experiments, profiles/shard_ab.py)
+static int resident_max_h() { const char* e = getenv("NERFATTN_RESIDENT_MAX_H"); return e ? atoi(e) : 128; }
+// NERFATTN_RESIDENT=1 sends every eligible group to the fit-resident kernel, whatever else is in the call (the tests
+// use it: their calls are too small for the planner below to pick it)
+static bool resident_forced() { const char* e = getenv("NERFATTN_RESIDENT"); return e && atoi(e) == 1; }
+
+// The fit-resident kernel is the cheapest way to train a narrow fit in SM-time (one SM per fit, no activation traffic),
+// but not in latency: a fit is a serial chain of row tiles, ~12.1 us (`small`) / ~7.5 us (`tiny`) per tile and epoch
+// on a B200, however few fits there are -- while the same fits take ~2 us each per epoch through the chain + dW
+// kernels (40 us at least), spread over all SMs.  So it pays exactly when its CTAs can hide beside enough other work:
+// measured on the shards of the 280-fit sweep (profiles/shard_ab.py), 280 / 140 / 70 fits per GPU: all narrow fits
+// resident is fastest; 35 fits per GPU (8 GPUs): `small` resident is the critical path (0.288 ms per epoch against
+// 0.244 with only `tiny` resident).  Rule: resident iff the group's epoch on its SMs takes at most 3/4 of the epoch of
+// everything that is not resident-eligible (estimated from its FLOPs at the sweep's measured rate); a call of narrow
+// fits only takes the kernel that finishes first.
+static bool resident_pays(int H, int mtiles, int nf_group, double rest_seconds_per_epoch) {
+    const double t_res = mtiles * (H <= 64 ? 7.5e-6 : 12.1e-6);
+    if (rest_seconds_per_epoch > 0) return t_res <= 0.75 * rest_seconds_per_epoch;
+    const double t_chain = std::max(40e-6, nf_group * (H <= 64 ? 1.8e-6 : 2.2e-6) * (mtiles / 16.0));
+    return t_res < t_chain;
+}
 
 // ------------------------------------------------------------------ planning
 struct Group {
@@ -174,11 +195,18 @@ static void make_plan(const na_fit_t* fits, int nfits, int epochs, int precision
 
     const bool bf = precision == NA_PREC_BF16;
     const size_t esz = bf ? 2 : 4;
+    auto resident_eligible = [&](const Group& g) {
+        return bf && resident_enabled() && g.H <= resident_max_h() && res::shape_supported(g.N, g.D, g.H, g.L);
+    };
+    double rest_seconds = 0;                                // one epoch of everything that cannot be fit-resident
+    for (const Group& g : plan.groups)
+        if (!resident_eligible(g))
+            rest_seconds += (double)g.fit_idx.size() * (6.0 * g.N * ((double)g.L * g.H * g.H + (double)g.H * g.D) + 4.0 * g.N * g.H) / 400e12;
     for (Group& g : plan.groups) {
         g.nf = (int)g.fit_idx.size();
         g.mtiles = ceil_div(g.N, 128);
         g.d_recs = ar.take<FitRec>(g.nf);
-        g.use_resident = bf && resident_enabled() && res::shape_supported(g.N, g.D, g.H, g.L);
+        g.use_resident = resident_eligible(g) && (resident_forced() || resident_pays(g.H, g.mtiles, g.nf, rest_seconds));
         g.use_chain = !g.use_resident && bf && chain_enabled() && chain::shape_supported(g.N, g.D, g.H, g.L);
         g.d_epoch = ar.take<int>(64);
         g.d_done = ar.take<unsigned int>(64);

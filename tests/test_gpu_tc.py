@@ -197,7 +197,10 @@ def test_resident_kernel_agrees_with_chain_path(cuda_device, monkeypatch, h, w, 
 
     def run(epochs, resident):
         monkeypatch.delenv('NERFATTN_NO_RESIDENT', raising=False)
-        if not resident:
+        monkeypatch.delenv('NERFATTN_RESIDENT', raising=False)
+        if resident:
+            monkeypatch.setenv('NERFATTN_RESIDENT', '1')     # a call this small would take the chain path by itself
+        else:
             monkeypatch.setenv('NERFATTN_NO_RESIDENT', '1')
         return gpu_fit(kv, cfg, epochs, 'bf16', state, keep_optimizer_state=True)
 
@@ -216,10 +219,11 @@ def test_resident_kernel_agrees_with_chain_path(cuda_device, monkeypatch, h, w, 
     assert again.losses == got.losses and torch.equal(flat(again.model.state_dict()), flat(got.model.state_dict()))
 
 
-def test_resident_groups_beside_epoch_graphs_and_progress(cuda_device):
+def test_resident_groups_beside_epoch_graphs_and_progress(cuda_device, monkeypatch):
     """A mixed sweep: tiny / small fits train in the fit-resident kernel on a side stream while the other architectures
     replay their epoch graphs; progress evaluations (siren.py:107-115) split both into the same stretches."""
     from nerf_attention.extract import synthetic_head
+    monkeypatch.setenv('NERFATTN_RESIDENT', '1')             # 14 short fits: the planner alone would not pick the kernel
     keys, values = synthetic_head(3, 1, 256, 32, 8, 128)
     spec = [(t, c, seeded_state(c, 128, 70 + i)) for t in (keys, values) for i, c in enumerate(na.CONFIGS_FULL)]
     jobs = [na.FitJob(t, c, model_from_state(c, 128, s)) for t, c, s in spec]
