@@ -1,6 +1,6 @@
 """Per-architecture throughput of the batched fit (40 fits of one architecture per call, like one
 group of the 280-fit sweep): fit-epochs/s and algorithmic TFLOP/s, CUDA-event timed.
-usage: python profiles/per_arch.py [epochs] [precision] [nfits]"""
+usage: python profiles/per_arch.py [epochs] [precision] [nfits] [arch,arch,..]"""
 import json
 import sys
 import time
@@ -15,10 +15,13 @@ from nerf_attention.extract import synthetic_head
 epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 prec = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 nfits = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+only = sys.argv[4].split(',') if len(sys.argv) > 4 else None
 N, D = 2048, 128
 tensors = [synthetic_head(16, h % 8, N, 32, 8, D)[h // 8 % 2] for h in range(16)]
 out = []
 for cfg in na.CONFIGS_FULL:
+    if only and cfg.name not in only:
+        continue
     H, L = cfg.hidden_features, cfg.hidden_layers
     flop = 6 * N * (L * H * H + H * D) + 4 * N * H
     torch.manual_seed(0)
