@@ -398,10 +398,10 @@ static void fp32_epoch(const Group& g, const Plan& plan, double b1, double b2, d
 //                and ends the group's epoch)                                                -- HBM-bound
 // max_ctas caps the persistent grids (0 = all SMs): the two-lane schedule runs the two halves of different groups
 // side by side on disjoint sets of SMs.
-static int chain_part(const Group& g, int max_ctas, cudaStream_t s) {
+static int chain_part(const Group& g, int max_ctas, cudaStream_t s, bool pack = false) {
     if (!(chain::phase_mask() & 1)) return NA_OK;
     return chain::train_step(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, g.cmaps, g.chain_scratch, g.losspart,
-                             g.losspart_per_fit, g.mtiles, g.psc, g.xpart, g.colpart + g.colpart_layer_off[0], max_ctas, s);
+                             g.losspart_per_fit, g.mtiles, g.psc, g.xpart, g.colpart + g.colpart_layer_off[0], max_ctas, s, pack);
 }
 static int update_part(const Group& g, const Plan& plan, double b1, double b2, double eps, int max_ctas, cudaStream_t s) {
     const int phases = chain::phase_mask();
@@ -713,10 +713,13 @@ extern "C" int nerfattn_fit_batched_ex(const na_fit_t* fits, int32_t nfits, int3
     // One epoch of one group, all of it on stream s (eager mode, fp32, unfused tensor path, single-group calls).
     // cap: most CTAs a persistent kernel of this epoch may use (0 = all SMs) -- while fit-resident kernels hold an SM
     // each, a 148-CTA persistent grid would run as two or three ragged waves on what is left
+    // several shape groups in one call compete for the SMs: launches that cannot fill both tile slots of every CTA are packed
+    // onto half the CTAs (chain::launch_h); NERFATTN_NO_PACK=1 keeps one tile per CTA
+    const bool contended = plan.groups.size() >= 2 && !env_flag("NERFATTN_NO_PACK");
     auto group_epoch = [&](const Group& g, cudaStream_t s, int cap) -> int {
         if (precision == NA_PREC_FP32) { fp32_epoch(g, plan, beta1, beta2, eps, s); return NA_OK; }
         if (g.use_chain) {
-            int r2 = chain_part(g, cap, s);
+            int r2 = chain_part(g, cap, s, contended);
             return r2 ? r2 : update_part(g, plan, beta1, beta2, eps, cap, s);
         }
         int r2 = tc::epoch(g.N, g.D, g.H, g.L, g.nf, g.lm, g.d_recs, *g.maps, g.act, g.cosb, g.dz, g.dy, g.gradpart,

@@ -1040,12 +1040,17 @@ inline cudaError_t launch_mode(int mode, int grid, const ChainMaps& maps, const 
 }
 // mode: 0 training, 1 decode logits, 2 decode values.  The 2-CTA cluster variant exists for training only.
 template <int H>
-inline int launch_h(const ChainMaps& maps, const ChainArgs& a_in, int mode, cudaStream_t s, int max_ctas = 0) {
+inline int launch_h(const ChainMaps& maps, const ChainArgs& a_in, int mode, cudaStream_t s, int max_ctas = 0, bool pack = false) {
     ChainArgs a = a_in;
     const int tiles = a.nf * a.mtiles;
     const bool cl = mode == 0 && use_cluster(a.N, H, a.D);
     int grid = std::min(tiles, (max_ctas > 0) ? std::min(max_ctas, num_sms()) : num_sms());
     if (cl) grid &= ~1;
+    // A launch that cannot fill both slots of every CTA: with other kernels competing for the SMs (`pack`: several shape
+    // groups in one call) two tiles on half the CTAs cost barely more time than one tile each -- the slots alternate -- and
+    // half the SM-time (the 35-fit shards of the 8-GPU sweep: 0.245 -> 0.231 ms per epoch); alone, one tile per CTA is the
+    // lower latency and stays
+    if (pack && mode == 0 && !cl && H <= 256 && slots_for(H) == 2 && tiles < 2 * grid) grid = ceil_div(tiles, 2);
     a.pair_tiles = (tiles >= 2 * grid && !getenv("NERFATTN_NO_PAIR_TILES")) ? 1 : 0;
     cudaError_t e;
     constexpr int NSD = (H <= 256) ? 2 : 1;                  // default slots
@@ -1057,12 +1062,12 @@ inline int launch_h(const ChainMaps& maps, const ChainArgs& a_in, int mode, cuda
     if (e != cudaSuccess) { set_error("chain_kernel launch failed: %s", cudaGetErrorString(e)); return NA_ERR_CUDA; }
     return NA_OK;
 }
-inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s, int max_ctas = 0) {
+inline int launch(int H, const ChainMaps& maps, const ChainArgs& a, int mode, cudaStream_t s, int max_ctas = 0, bool pack = false) {
     switch (H) {
-        case 64: return launch_h<64>(maps, a, mode, s, max_ctas);
-        case 128: return launch_h<128>(maps, a, mode, s, max_ctas);
-        case 256: return launch_h<256>(maps, a, mode, s, max_ctas);
-        case 512: return launch_h<512>(maps, a, mode, s, max_ctas);
+        case 64: return launch_h<64>(maps, a, mode, s, max_ctas, pack);
+        case 128: return launch_h<128>(maps, a, mode, s, max_ctas, pack);
+        case 256: return launch_h<256>(maps, a, mode, s, max_ctas, pack);
+        case 512: return launch_h<512>(maps, a, mode, s, max_ctas, pack);
         default: set_error("chain: unsupported H %d", H); return NA_ERR_UNSUPPORTED;
     }
 }
@@ -1112,7 +1117,7 @@ inline void scale_params(const FitRec* recs, int n, int H, int L, float* psc, cu
 // The weight gradients and Adam follow in dw::dw_adam_kernel (siren_dw.cuh), the layer-0 parameters in adam_kernel.
 inline int train_step(int N, int D, int H, int L, int nf, const LayerMap& lm, const FitRec* recs, const ChainMaps& cm,
                       __nv_bfloat16* scratch, float* losspart, int losspart_per_fit, int mtiles, const float* psc,
-                      float* xpart, float* colpart0, int max_ctas, cudaStream_t s) {
+                      float* xpart, float* colpart0, int max_ctas, cudaStream_t s, bool pack = false) {
     ChainArgs a{};
     a.N = N; a.D = D; a.L = L; a.nf = nf; a.mtiles = mtiles; a.recs = recs;
     for (int l = 0; l <= L + 1; ++l) { a.w_off[l] = lm.w_off[l]; a.b_off[l] = lm.b_off[l]; }
@@ -1123,7 +1128,7 @@ inline int train_step(int N, int D, int H, int L, int nf, const LayerMap& lm, co
     a.psc = psc; a.psc_fit = (int)psc_floats(H, L);
     a.xpart = xpart; a.colpart0 = colpart0;
     a.dbg = chain_dbg();
-    return launch(H, cm, a, 0, s, max_ctas);
+    return launch(H, cm, a, 0, s, max_ctas, pack);
 }
 
 // Forward-only chain for the fused decode: partial scores [n][CG][N] (decode_finish sums them).

@@ -21,9 +21,9 @@ for j in jobs:
     flat = torch.empty(j.model.count_parameters(), dtype=torch.float32)
     batched.pack_model(j.model, flat)
     initial.append(flat)
-variants = [('default', {}), ('no_resident', {'NERFATTN_NO_RESIDENT': '1'}), ('resident_tiny_only', {'NERFATTN_RESIDENT_MAX_H': '64'})]
+variants = [('default', {}), ('no_pack', {'NERFATTN_NO_PACK': '1'}), ('no_resident', {'NERFATTN_NO_RESIDENT': '1'})]
 for name, env in variants * 2:
-    for k in ('NERFATTN_NO_RESIDENT', 'NERFATTN_RESIDENT_MAX_H'):
+    for k in ('NERFATTN_NO_RESIDENT', 'NERFATTN_RESIDENT_MAX_H', 'NERFATTN_NO_PACK'):
         os.environ.pop(k, None)
     os.environ.update(env)
     for j, flat in zip(jobs, initial):
