@@ -1,5 +1,6 @@
 """One rank's shard of the strong-scaled sweep, alone on one GPU: device time per epoch for a few library knobs.
-usage: python profiles/shard_ab.py [world=8] [rank=0] [epochs=400]   (env knobs are set per variant inside)"""
+usage: python profiles/shard_ab.py [world=8] [rank=0] [epochs=400] [single]   (env knobs are set per variant inside;
+"single": one variant, the knobs of the calling environment -- for knobs that are read once per process)"""
 import json
 import os
 import sys
@@ -21,11 +22,15 @@ for j in jobs:
     flat = torch.empty(j.model.count_parameters(), dtype=torch.float32)
     batched.pack_model(j.model, flat)
     initial.append(flat)
+single = len(sys.argv) > 4 and sys.argv[4] == 'single'
 variants = [('default', {}), ('no_pack', {'NERFATTN_NO_PACK': '1'}), ('no_resident', {'NERFATTN_NO_RESIDENT': '1'})]
+if single:
+    variants = [(' '.join(f'{k}={v}' for k, v in sorted(os.environ.items()) if k.startswith('NERFATTN_')) or 'default', None)]
 for name, env in variants * 2:
-    for k in ('NERFATTN_NO_RESIDENT', 'NERFATTN_RESIDENT_MAX_H', 'NERFATTN_NO_PACK'):
-        os.environ.pop(k, None)
-    os.environ.update(env)
+    if env is not None:
+        for k in ('NERFATTN_NO_RESIDENT', 'NERFATTN_RESIDENT_MAX_H', 'NERFATTN_NO_PACK'):
+            os.environ.pop(k, None)
+        os.environ.update(env)
     for j, flat in zip(jobs, initial):
         batched.adopt_packed(j.model, flat)
     b = batched.FitBatch(jobs, epochs=epochs, device='cuda', precision='bf16', keep_initial=True)
