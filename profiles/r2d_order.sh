@@ -1,6 +1,8 @@
 #!/bin/bash
 # branch order (longest tile first) and branch priorities of the epoch graph: shards of the strong-scaled sweep alone on
 # one GPU (35 / 70 / 140 fits) and the whole 280-fit sweep, old behaviour (ORDER=0 PRIO=0) against the knobs
+# (the NERFATTN_ORDER / NERFATTN_PRIO hooks existed only in the build this script measured: neutral, patch not kept --
+#  DESIGN.md section 8; profiles/order_prio_ab_r02.log)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
 for world in 8 4 2; do
